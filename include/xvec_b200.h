@@ -1,0 +1,137 @@
+/* xvec_b200.h — C ABI of the B200-native x-vector extraction path (libxvec_b200.so).
+ *
+ * The reference (TorbenHellriegel/Speaker-Recognition-x-vectors) has no FFI / plugin registry: its boundary
+ * is the PyTorch nn.Module surface (tdnn_layer.py:5-41 TdnnLayer, main.py:23-94 XVectorModel).  These entry
+ * points are what a binding for that surface calls; each names the reference code it replaces.  The Python
+ * mirror of the module surface lives in speaker-recognition-x-vectors_b200/{tdnn_layer,xvector}.py and
+ * reaches this library through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `*_dev` pointer is DEVICE memory owned by the caller, `*_host` is host memory
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without synchronising
+ *   - return 0 on success, a negative XVEC_E_* code otherwise; xvec_last_error() describes the last failure of
+ *     the calling thread.  Nothing throws across the ABI.  There is no CPU fallback: a device that is not
+ *     sm_100 yields XVEC_E_DEVICE.
+ *   - frames are laid out as ONE flat row-major frame matrix (total_frames x channels): utterance u occupies
+ *     rows [start_u, start_u + T_u).  A TDNN layer computes output row r from input rows r + offset_j, so
+ *     every layer keeps the same row indexing; the last (c_last - c_0) rows of each utterance become
+ *     don't-care rows that pooling masks out.  No unfolded (time-context) tensor is ever written to memory.
+ */
+#ifndef XVEC_B200_H_
+#define XVEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XVEC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define XVEC_API __attribute__((visibility("default")))
+#else
+#define XVEC_API
+#endif
+
+/* element types of activations / packed weights */
+#define XVEC_F32 0  /* float32 storage, tensor-core math in TF32 (kind::tf32), fp32 accumulate */
+#define XVEC_BF16 1 /* bfloat16 storage, kind::f16 bf16 math, fp32 accumulate */
+
+#define XVEC_OK 0
+#define XVEC_E_ARG (-1)    /* bad shape / alignment / null pointer */
+#define XVEC_E_CUDA (-2)   /* a CUDA runtime or driver call failed */
+#define XVEC_E_DEVICE (-3) /* current device is not compute capability 10.x */
+
+#define XVEC_MAX_TAPS 8
+#define XVEC_TILE_N 256     /* output-channel tile; packed weights are padded to a multiple of this many rows */
+#define XVEC_POOL_BLOCK 32  /* rows per pooling partial block of the fused TDNN5+pool epilogue */
+#define XVEC_POOL_CHUNK 128 /* rows per partial of the standalone statistics-pooling kernel */
+
+XVEC_API int xvec_abi_version(void);
+XVEC_API const char* xvec_last_error(void);
+/* 0 if the current CUDA device can run these kernels (compute capability 10.x), else XVEC_E_DEVICE. */
+XVEC_API int xvec_device_check(void);
+/* Value left by the device-side pipeline watchdog (0 = never fired). Synchronises the device. */
+XVEC_API int xvec_watchdog_code(void);
+
+/* Number of K elements one packed weight row holds: taps * ceil(cin / kc) * kc, kc = 32 (F32) or 64 (BF16). */
+XVEC_API int64_t xvec_packed_k(int cin, int taps, int dtype);
+/* Rows of a packed weight matrix: n rounded up to XVEC_TILE_N. */
+XVEC_API int64_t xvec_packed_n(int n);
+
+/* Pack a Linear weight for xvec_tdnn_layer.
+ * replaces: the layout nn.Linear(input_size*len(context), output_size) stores (tdnn_layer.py:19): W (n, taps*cin)
+ * row-major, column index = tap*cin + channel (context-major, because of torch.cat(..., 2) at tdnn_layer.py:29).
+ * w_dev: float32 (n, taps*cin).  out_dev: (xvec_packed_n(n), xvec_packed_k(cin,taps,dtype)) of `dtype`, zero padded. */
+XVEC_API int xvec_pack_weight(const float* w_dev, int n, int taps, int cin, int dtype, void* out_dev, void* stream);
+
+/* One TDNN layer on the flat frame matrix, no unfold in memory:
+ *   y[r, :] = bn( relu( sum_j W_j . x[r + tap_offsets[j], :] + bias ) ),  r in [0, rows)
+ * replaces: TdnnLayer.forward (tdnn_layer.py:26-41) = get_time_context (tdnn_layer.py:43-60) + torch.cat +
+ * nn.Linear + ReLU + eval-mode BatchNorm1d; with taps == 1 and relu/bn optional it is also nn.Linear
+ * (segment_layer6/7, output: main.py:45-47, 87-90, 71-74).
+ *   x_dev      (x_rows, cin) of x_dtype, row stride x_ld elements (x_ld*elsize multiple of 16 bytes, base 16-byte aligned)
+ *   w_packed   from xvec_pack_weight with the same taps/cin/dtype
+ *   tap_offsets_host  taps non-negative row offsets c_j - c_0 (HOST array)
+ *   bias_dev   float32 (n) or NULL;  bn_scale_dev/bn_shift_dev float32 (n) or both NULL:
+ *              scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale
+ *   y_dev      (rows, n) of y_dtype, row stride y_ld elements.  Input rows beyond x_rows read as zero.
+ */
+XVEC_API int xvec_tdnn_layer(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld,
+                    const void* w_packed_dev, int n, const int32_t* tap_offsets_host, int taps,
+                    const float* bias_dev, const float* bn_scale_dev, const float* bn_shift_dev, int relu,
+                    void* y_dev, int y_dtype, int64_t y_ld, int64_t rows, void* stream);
+
+/* Last TDNN layer fused with the first half of statistics pooling: the (rows x n) activation
+ * r = relu(W.x + bias) is never written; per XVEC_POOL_BLOCK-row block and utterance the kernel emits column sums of
+ * r and r*r into part_dev[slot][2][n] (float32).  BatchNorm of this layer is applied by xvec_pool_finalize.
+ * replaces: TdnnLayer #5 (main.py:43) + the reads of torch.mean/torch.std in stat_pool (main.py:59-63).
+ *   row_utt_dev        int32 (rows): utterance index of a row that takes part in pooling, -1 for don't-care rows
+ *   blk_slot_base_dev  int32 (ceil(rows/128)*4): first partial slot of each 32-row block (slots of a block are
+ *                      consecutive, one per utterance with a pooled row in it, in row order)
+ */
+XVEC_API int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld,
+                         const void* w_packed_dev, int n, const int32_t* tap_offsets_host, int taps,
+                         const float* bias_dev, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev,
+                         float* part_dev, int64_t rows, void* stream);
+
+/* Standalone statistics pooling, first half (bandwidth-bound streaming reduction): for utterance u and chunk j,
+ * column sums of x and x*x over rows [row_start[u] + j*XVEC_POOL_CHUNK, ...) -> part_dev[slot_start[u] + j][2][p].
+ * replaces: the reads of torch.mean / torch.std in XVectorModel.stat_pool (main.py:59-63) on a materialised
+ * (B, T', p) activation; ragged lengths are an extension (the reference pads/cuts to 3 s, dataset.py:204).
+ *   x_dev (.., p) of x_dtype with row stride x_ld elements; p multiple of 4
+ *   row_start_dev int64 (n_utts), n_rows_dev int32 (n_utts), slot_start_dev int32 (n_utts+1) = exclusive prefix
+ *   sum of ceil(n_rows/XVEC_POOL_CHUNK); max_chunks = max over utterances of that count.
+ */
+XVEC_API int xvec_stats_pool_partial(const void* x_dev, int x_dtype, int64_t x_ld, int p, const int64_t* row_start_dev,
+                            const int32_t* n_rows_dev, const int32_t* slot_start_dev, int n_utts, int max_chunks,
+                            float* part_dev, void* stream);
+
+/* Statistics pooling, second half: deterministic fixed-order (float64) reduction of an utterance's partial slots
+ * [slot_start[u], slot_start[u+1]) and the final statistics
+ *   mean = s*(S/n) + h,   std = |s| * sqrt( (Q - S*S/n) / (n-1) )       (unbiased, torch.std default; n==1 -> NaN)
+ * replaces: torch.mean, torch.std, torch.cat in stat_pool (main.py:60-62) (+ the BatchNorm of TDNN5 folded
+ * through the statistics when bn_scale/shift are given; both NULL = plain pooling).
+ *   out_f32_dev float32 (n_utts, 2p) [mean || std], row stride 2p;  out_lp_dev optional second copy in out_lp_dtype
+ *   with row stride out_lp_ld (feeds segment_layer6 directly), or NULL.
+ */
+XVEC_API int xvec_pool_finalize(const float* part_dev, const int32_t* slot_start_dev, const int32_t* n_rows_dev, int n_utts,
+                       int p, const float* bn_scale_dev, const float* bn_shift_dev, float* out_f32_dev,
+                       void* out_lp_dev, int out_lp_dtype, int64_t out_lp_ld, void* stream);
+
+/* float32 -> dtype copy of a (rows, cols) matrix (row strides in elements); XVEC_F32 is a strided copy.
+ * replaces: samples.float() (main.py:137) for the bf16 pipeline. */
+XVEC_API int xvec_cast(const float* src_dev, int64_t src_ld, void* dst_dev, int dst_dtype, int64_t dst_ld, int64_t rows,
+              int cols, void* stream);
+
+/* Cosine score of each trial: out[i] = <a,b>/(|a||b|) with a = xvec[enrol[i]], b = xvec[test[i]] (float32 in,
+ * float32 out, float32 accumulation).  BASELINE.json config 5; the reference scores with PLDA on the full NxN
+ * matrix and picks trial entries afterwards (plda_score_stat.py:59-87). */
+XVEC_API int xvec_cosine_trials(const float* xvec_dev, int64_t ld, int dim, const int32_t* enrol_dev, const int32_t* test_dev,
+                       int64_t n_trials, float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XVEC_B200_H_ */

@@ -1,0 +1,100 @@
+"""ctypes binding of libxvec_b200.so (C ABI in include/xvec_b200.h).
+
+The library is the product's only compute path.  If it cannot be loaded (or built) every entry point
+raises — there is deliberately no PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libxvec_b200.so")
+
+F32, BF16 = 0, 1
+E_ARG, E_CUDA, E_DEVICE = -1, -2, -3
+TILE_N, POOL_BLOCK, POOL_CHUNK, MAX_TAPS = 256, 32, 128, 8
+ABI_VERSION = 1
+
+_SIGNATURES = {
+    "xvec_abi_version": (c_int, []),
+    "xvec_last_error": (c_char_p, []),
+    "xvec_device_check": (c_int, []),
+    "xvec_watchdog_code": (c_int, []),
+    "xvec_packed_k": (c_int64, [c_int, c_int, c_int]),
+    "xvec_packed_n": (c_int64, [c_int]),
+    "xvec_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "xvec_tdnn_layer": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int, POINTER(c_int32), c_int,
+                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    "xvec_tdnn_pool_fused": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int, POINTER(c_int32), c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "xvec_stats_pool_partial": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                        c_void_p, c_void_p]),
+    "xvec_pool_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_int64, c_void_p]),
+    "xvec_cast": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p]),
+    "xvec_cosine_trials": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lock = threading.Lock()
+_lib = None
+
+
+class XvecError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libxvec_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load (building in-tree with nvcc if the .so is absent) and type the library."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise ImportError(f"{LIB_PATH} is missing; run speaker-recognition-x-vectors_b200/build.py")
+            from . import build as _build
+            _build.build()
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if lib.xvec_abi_version() != ABI_VERSION:
+            raise ImportError(f"{LIB_PATH}: ABI {lib.xvec_abi_version()} != expected {ABI_VERSION}; rebuild")
+        _lib = lib
+        return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise XvecError(rc, load().xvec_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None passes NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+    if torch_dtype == torch.float32:
+        return F32
+    if torch_dtype == torch.bfloat16:
+        return BF16
+    raise ValueError(f"unsupported dtype {torch_dtype}; the kernels take float32 (TF32 math) or bfloat16")
+
+
+def taps_array(offsets):
+    arr = (c_int32 * len(offsets))(*[int(o) for o in offsets])
+    return arr

@@ -1,0 +1,104 @@
+// extern "C" surface of libxvec_b200.so (declared in include/xvec_b200.h) + small host utilities.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "xvec_internal.h"
+
+namespace xvec {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+namespace {
+struct DevInfo {
+  int checked = 0;  // 0 unknown, 1 ok, -1 unsupported
+  int sms = 0;
+  int major = 0, minor = 0;
+};
+DevInfo g_dev[64];
+
+DevInfo* cur_dev() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
+  DevInfo* di = &g_dev[d];
+  if (!di->checked) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d) != cudaSuccess) return nullptr;
+    di->sms = prop.multiProcessorCount;
+    di->major = prop.major;
+    di->minor = prop.minor;
+    di->checked = (prop.major == 10) ? 1 : -1;
+  }
+  return di;
+}
+}  // namespace
+
+int device_check() {
+  DevInfo* di = cur_dev();
+  if (!di) return set_error(XVEC_E_CUDA, "no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+  if (di->checked < 0)
+    return set_error(XVEC_E_DEVICE, "device is sm_%d%d; these kernels are built for sm_100a only (no fallback)", di->major, di->minor);
+  return XVEC_OK;
+}
+
+int num_sms() {
+  DevInfo* di = cur_dev();
+  return di ? di->sms : 1;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+}  // namespace xvec
+
+using namespace xvec;
+
+extern "C" {
+
+int xvec_abi_version(void) { return XVEC_ABI_VERSION; }
+const char* xvec_last_error(void) { return g_err; }
+int xvec_device_check(void) { return device_check(); }
+int xvec_watchdog_code(void) {
+  cudaDeviceSynchronize();
+  return read_watchdog();
+}
+
+int64_t xvec_packed_k(int cin, int taps, int dtype) {
+  const int kc = dtype == XVEC_BF16 ? 64 : 32;
+  return static_cast<int64_t>(taps) * ((cin + kc - 1) / kc) * kc;
+}
+int64_t xvec_packed_n(int n) { return static_cast<int64_t>((n + XVEC_TILE_N - 1) / XVEC_TILE_N) * XVEC_TILE_N; }
+
+int xvec_tdnn_layer(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld, const void* w_packed_dev, int n,
+                    const int32_t* tap_offsets_host, int taps, const float* bias_dev, const float* bn_scale_dev,
+                    const float* bn_shift_dev, int relu, void* y_dev, int y_dtype, int64_t y_ld, int64_t rows, void* stream) {
+  if (!tap_offsets_host) return set_error(XVEC_E_ARG, "tap_offsets_host is NULL");
+  return gemm_dispatch(x_dev, x_dtype, x_rows, cin, x_ld, w_packed_dev, n, tap_offsets_host, taps, bias_dev, bn_scale_dev,
+                       bn_shift_dev, relu, y_dev, y_dtype, y_ld, nullptr, nullptr, nullptr, rows, false, stream);
+}
+
+int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld, const void* w_packed_dev, int n,
+                         const int32_t* tap_offsets_host, int taps, const float* bias_dev, const int32_t* row_utt_dev,
+                         const int32_t* blk_slot_base_dev, float* part_dev, int64_t rows, void* stream) {
+  if (!tap_offsets_host) return set_error(XVEC_E_ARG, "tap_offsets_host is NULL");
+  return gemm_dispatch(x_dev, x_dtype, x_rows, cin, x_ld, w_packed_dev, n, tap_offsets_host, taps, bias_dev, nullptr, nullptr, 1,
+                       nullptr, XVEC_F32, 0, row_utt_dev, blk_slot_base_dev, part_dev, rows, true, stream);
+}
+
+}  // extern "C"

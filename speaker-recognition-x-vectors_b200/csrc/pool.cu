@@ -1,0 +1,269 @@
+// Bandwidth-bound kernels of the extraction path: standalone statistics pooling (partial + finalize), the
+// float32 -> bf16 cast, weight packing and per-trial cosine scoring.  sm_100a build; plain coalesced streaming code —
+// these are HBM/L2-bound reductions, not tensor-core work.
+#include <cuda_bf16.h>
+
+#include "xvec_internal.h"
+
+namespace xvec {
+
+// ------------------------------------------------------------------------------------------------ stats pooling
+// grid = (n_utts, max_chunks, ceil(p / 512)), block = 128: thread owns 4 adjacent columns, the CTA streams
+// XVEC_POOL_CHUNK rows of one utterance; every row read is one contiguous <= 2 KiB segment per CTA.
+template <bool kBf16>
+__global__ void __launch_bounds__(128)
+stats_pool_partial_kernel(const void* __restrict__ x, long long ld, int p, const long long* __restrict__ row_start,
+                          const int* __restrict__ n_rows, const int* __restrict__ slot_start, float* __restrict__ part) {
+  const int u = blockIdx.x;
+  const int nr = n_rows[u];
+  const int r0 = blockIdx.y * XVEC_POOL_CHUNK;
+  if (r0 >= nr) return;
+  const int r1 = min(nr, r0 + XVEC_POOL_CHUNK);
+  const int c = (blockIdx.z * 128 + threadIdx.x) * 4;
+  if (c >= p) return;
+  const long long first = row_start[u] + r0;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  constexpr int U = 8;  // independent row loads in flight per thread
+  int r = r0;
+  if constexpr (kBf16) {
+    const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + first * ld + c);
+    const long long step = ld / 4;  // uint2 = 4 bf16
+    for (; r + U <= r1; r += U) {
+      uint2 v[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) v[i] = __ldcs(src + static_cast<long long>(r - r0 + i) * step);
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[i].x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[i].y));
+        s0 += a.x; s1 += a.y; s2 += b.x; s3 += b.y;
+        q0 = fmaf(a.x, a.x, q0); q1 = fmaf(a.y, a.y, q1); q2 = fmaf(b.x, b.x, q2); q3 = fmaf(b.y, b.y, q3);
+      }
+    }
+    for (; r < r1; ++r) {
+      const uint2 w = __ldcs(src + static_cast<long long>(r - r0) * step);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+      s0 += a.x; s1 += a.y; s2 += b.x; s3 += b.y;
+      q0 = fmaf(a.x, a.x, q0); q1 = fmaf(a.y, a.y, q1); q2 = fmaf(b.x, b.x, q2); q3 = fmaf(b.y, b.y, q3);
+    }
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + first * ld + c);
+    const long long step = ld / 4;
+    for (; r + U <= r1; r += U) {
+      float4 v[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) v[i] = __ldcs(src + static_cast<long long>(r - r0 + i) * step);
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        s0 += v[i].x; s1 += v[i].y; s2 += v[i].z; s3 += v[i].w;
+        q0 = fmaf(v[i].x, v[i].x, q0); q1 = fmaf(v[i].y, v[i].y, q1);
+        q2 = fmaf(v[i].z, v[i].z, q2); q3 = fmaf(v[i].w, v[i].w, q3);
+      }
+    }
+    for (; r < r1; ++r) {
+      const float4 w = __ldcs(src + static_cast<long long>(r - r0) * step);
+      s0 += w.x; s1 += w.y; s2 += w.z; s3 += w.w;
+      q0 = fmaf(w.x, w.x, q0); q1 = fmaf(w.y, w.y, q1); q2 = fmaf(w.z, w.z, q2); q3 = fmaf(w.w, w.w, q3);
+    }
+  }
+  float* dst = part + static_cast<size_t>(slot_start[u] + blockIdx.y) * 2 * p + c;
+  *reinterpret_cast<float4*>(dst) = make_float4(s0, s1, s2, s3);
+  *reinterpret_cast<float4*>(dst + p) = make_float4(q0, q1, q2, q3);
+}
+
+// grid = (n_utts, ceil(p/128)), block = 128: fixed-order float64 reduction of an utterance's partial slots.
+__global__ void __launch_bounds__(128)
+pool_finalize_kernel(const float* __restrict__ part, const int* __restrict__ slot_start, const int* __restrict__ n_rows, int p,
+                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out,
+                     void* __restrict__ out_lp, int lp_dtype, long long lp_ld) {
+  const int u = blockIdx.x;
+  const int col = blockIdx.y * 128 + threadIdx.x;
+  if (col >= p) return;
+  const int sl0 = slot_start[u], sl1 = slot_start[u + 1];
+  double S = 0.0, Q = 0.0;
+  for (int sl = sl0; sl < sl1; ++sl) {
+    const float* src = part + static_cast<size_t>(sl) * 2 * p + col;
+    S += static_cast<double>(src[0]);
+    Q += static_cast<double>(src[p]);
+  }
+  const int n = n_rows[u];
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double mean = n > 0 ? S / n : nan;
+  double var = n > 1 ? (Q - S * S / n) / (n - 1) : nan;  // torch.std: unbiased; a single frame gives NaN
+  if (var < 0.0) var = 0.0;
+  const float sc = scale ? scale[col] : 1.f;
+  const float sh = shift ? shift[col] : 0.f;
+  const float m = static_cast<float>(mean * sc + sh);
+  const float sd = static_cast<float>(fabs(static_cast<double>(sc)) * sqrt(var));
+  out[static_cast<size_t>(u) * 2 * p + col] = m;
+  out[static_cast<size_t>(u) * 2 * p + p + col] = sd;
+  if (out_lp) {
+    if (lp_dtype == XVEC_BF16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_lp) + static_cast<size_t>(u) * lp_ld;
+      o[col] = __float2bfloat16_rn(m);
+      o[p + col] = __float2bfloat16_rn(sd);
+    } else {
+      float* o = reinterpret_cast<float*>(out_lp) + static_cast<size_t>(u) * lp_ld;
+      o[col] = m;
+      o[p + col] = sd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cast / pack
+__global__ void cast_kernel(const float* __restrict__ src, long long src_ld, void* __restrict__ dst, int dst_dtype, long long dst_ld,
+                            long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const float v = src[r * src_ld + c];
+    if (dst_dtype == XVEC_BF16)
+      reinterpret_cast<__nv_bfloat16*>(dst)[r * dst_ld + c] = __float2bfloat16_rn(v);
+    else
+      reinterpret_cast<float*>(dst)[r * dst_ld + c] = v;
+  }
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, int n, int taps, int cin, int tap_k, long long n_pad, long long k_pad,
+                                   int dtype, void* __restrict__ out) {
+  const long long total = n_pad * k_pad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / k_pad;
+    const int kk = static_cast<int>(i - row * k_pad);
+    const int tap = kk / tap_k;
+    const int ch = kk - tap * tap_k;
+    const float v = (row < n && ch < cin) ? w[row * (static_cast<long long>(taps) * cin) + tap * cin + ch] : 0.f;
+    if (dtype == XVEC_BF16)
+      reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    else
+      reinterpret_cast<float*>(out)[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cosine trials
+// one warp per trial
+__global__ void __launch_bounds__(256)
+cosine_trials_kernel(const float* __restrict__ xv, long long ld, int dim, const int* __restrict__ enrol, const int* __restrict__ test,
+                     long long n_trials, float* __restrict__ out) {
+  const long long t = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= n_trials) return;
+  const float* a = xv + static_cast<long long>(enrol[t]) * ld;
+  const float* b = xv + static_cast<long long>(test[t]) * ld;
+  float ab = 0.f, aa = 0.f, bb = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    const float x = a[i], y = b[i];
+    ab = fmaf(x, y, ab);
+    aa = fmaf(x, x, aa);
+    bb = fmaf(y, y, bb);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    aa += __shfl_xor_sync(0xffffffffu, aa, o);
+    bb += __shfl_xor_sync(0xffffffffu, bb, o);
+  }
+  if (lane == 0) out[t] = ab * rsqrtf(aa) * rsqrtf(bb);
+}
+
+static int grid_for(long long total) {
+  const long long want = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(want < cap ? want : cap);
+}
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
+  return XVEC_OK;
+}
+
+}  // namespace xvec
+
+using namespace xvec;
+
+extern "C" {
+
+int xvec_stats_pool_partial(const void* x_dev, int x_dtype, int64_t x_ld, int p, const int64_t* row_start_dev,
+                            const int32_t* n_rows_dev, const int32_t* slot_start_dev, int n_utts, int max_chunks, float* part_dev,
+                            void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!x_dev || !row_start_dev || !n_rows_dev || !slot_start_dev || !part_dev) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (x_dtype != XVEC_F32 && x_dtype != XVEC_BF16) return set_error(XVEC_E_ARG, "bad x_dtype %d", x_dtype);
+  if (p <= 0 || p % 4 != 0 || x_ld % 4 != 0 || x_ld < p) return set_error(XVEC_E_ARG, "p and x_ld must be positive multiples of 4, x_ld >= p");
+  const int align = x_dtype == XVEC_BF16 ? 8 : 16;
+  if ((reinterpret_cast<uintptr_t>(x_dev) % align) != 0 || (reinterpret_cast<uintptr_t>(part_dev) & 15u) != 0)
+    return set_error(XVEC_E_ARG, "x_dev / part_dev are not sufficiently aligned");
+  if (n_utts <= 0 || max_chunks <= 0 || max_chunks > 65535) return set_error(XVEC_E_ARG, "bad n_utts / max_chunks");
+  dim3 grid(n_utts, max_chunks, (p + 511) / 512);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_dtype == XVEC_BF16)
+    stats_pool_partial_kernel<true><<<grid, 128, 0, st>>>(x_dev, x_ld, p, reinterpret_cast<const long long*>(row_start_dev), n_rows_dev,
+                                                         slot_start_dev, part_dev);
+  else
+    stats_pool_partial_kernel<false><<<grid, 128, 0, st>>>(x_dev, x_ld, p, reinterpret_cast<const long long*>(row_start_dev), n_rows_dev,
+                                                          slot_start_dev, part_dev);
+  return check_launch("stats_pool_partial_kernel");
+}
+
+int xvec_pool_finalize(const float* part_dev, const int32_t* slot_start_dev, const int32_t* n_rows_dev, int n_utts, int p,
+                       const float* bn_scale_dev, const float* bn_shift_dev, float* out_f32_dev, void* out_lp_dev, int out_lp_dtype,
+                       int64_t out_lp_ld, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!part_dev || !slot_start_dev || !n_rows_dev || !out_f32_dev) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (n_utts <= 0 || p <= 0) return set_error(XVEC_E_ARG, "non-positive size");
+  if ((bn_scale_dev == nullptr) != (bn_shift_dev == nullptr)) return set_error(XVEC_E_ARG, "bn_scale and bn_shift must be given together");
+  if (out_lp_dev && (out_lp_dtype != XVEC_F32 && out_lp_dtype != XVEC_BF16)) return set_error(XVEC_E_ARG, "bad out_lp_dtype");
+  if (out_lp_dev && out_lp_ld < 2 * p) return set_error(XVEC_E_ARG, "out_lp_ld < 2p");
+  dim3 grid(n_utts, (p + 127) / 128);
+  pool_finalize_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(part_dev, slot_start_dev, n_rows_dev, p, bn_scale_dev,
+                                                                            bn_shift_dev, out_f32_dev, out_lp_dev, out_lp_dtype, out_lp_ld);
+  return check_launch("pool_finalize_kernel");
+}
+
+int xvec_cast(const float* src_dev, int64_t src_ld, void* dst_dev, int dst_dtype, int64_t dst_ld, int64_t rows, int cols, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!src_dev || !dst_dev) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (rows <= 0 || cols <= 0 || src_ld < cols || dst_ld < cols) return set_error(XVEC_E_ARG, "bad shape");
+  if (dst_dtype != XVEC_F32 && dst_dtype != XVEC_BF16) return set_error(XVEC_E_ARG, "bad dst_dtype");
+  const long long total = rows * cols;
+  const int blocks = grid_for(total);
+  cast_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src_dev, src_ld, dst_dev, dst_dtype, dst_ld, rows, cols);
+  return check_launch("cast_kernel");
+}
+
+int xvec_pack_weight(const float* w_dev, int n, int taps, int cin, int dtype, void* out_dev, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!w_dev || !out_dev) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (n <= 0 || cin <= 0 || taps < 1 || taps > XVEC_MAX_TAPS) return set_error(XVEC_E_ARG, "bad shape");
+  if (dtype != XVEC_F32 && dtype != XVEC_BF16) return set_error(XVEC_E_ARG, "bad dtype");
+  const long long k_pad = xvec_packed_k(cin, taps, dtype);
+  const long long n_pad = xvec_packed_n(n);
+  const long long total = n_pad * k_pad;
+  const int blocks = grid_for(total);
+  pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w_dev, n, taps, cin, static_cast<int>(k_pad / taps), n_pad,
+                                                                           k_pad, dtype, out_dev);
+  return check_launch("pack_weight_kernel");
+}
+
+int xvec_cosine_trials(const float* xvec_dev, int64_t ld, int dim, const int32_t* enrol_dev, const int32_t* test_dev, int64_t n_trials,
+                       float* out_dev, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!xvec_dev || !enrol_dev || !test_dev || !out_dev) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (dim <= 0 || ld < dim || n_trials <= 0) return set_error(XVEC_E_ARG, "bad shape");
+  const long long blocks = (n_trials * 32 + 255) / 256;
+  cosine_trials_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(xvec_dev, ld, dim, enrol_dev, test_dev,
+                                                                                                   n_trials, out_dev);
+  return check_launch("cosine_trials_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+// Host-side helpers shared by the translation units of libxvec_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/xvec_b200.h"
+
+namespace xvec {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Records a message for xvec_last_error() (thread local) and returns `code`.
+int set_error(int code, const char* fmt, ...);
+// XVEC_OK when the current device is compute capability 10.x.
+int device_check();
+int num_sms();
+// Driver entry point for tensor-map creation, resolved through the runtime (no link-time libcuda dependency).
+PFN_encodeTiled get_encode_tiled();
+
+int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x_ld, const void* w_packed, int n,
+                  const int32_t* tap_offsets, int taps, const float* bias, const float* scale, const float* shift, int relu,
+                  void* y, int y_dtype, int64_t y_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part,
+                  int64_t rows, bool pool, void* stream);
+int read_watchdog();
+
+}  // namespace xvec

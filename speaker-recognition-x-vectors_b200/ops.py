@@ -1,0 +1,155 @@
+"""Functional wrappers: torch CUDA tensors in, C-ABI calls on the current CUDA stream, torch CUDA tensors out.
+
+torch is plumbing here (device memory, streams); every FLOP and every reduction happens in libxvec_b200.so.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, check, dtype_code, ptr, stream_ptr, taps_array
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise ValueError("xvec_b200 has no CPU path: tensors must live on a CUDA device")
+
+
+def _rowmajor_2d(t: torch.Tensor, what: str):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{what} must be a 2-D tensor with unit stride in the last dimension")
+    return t.stride(0)
+
+
+def pack_weight(weight: torch.Tensor, taps: int, cin: int, dtype: torch.dtype) -> torch.Tensor:
+    """nn.Linear weight (n, taps*cin) float32 -> packed (n_pad, k_pad) operand for xvec_tdnn_layer."""
+    _require_cuda(weight)
+    lib = _lib.load()
+    w = weight.detach().to(torch.float32).contiguous()
+    n = w.shape[0]
+    if w.shape[1] != taps * cin:
+        raise ValueError(f"weight has {w.shape[1]} columns, expected taps*cin = {taps * cin}")
+    code = dtype_code(dtype)
+    out = torch.empty((lib.xvec_packed_n(n), lib.xvec_packed_k(cin, taps, code)), dtype=dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib.xvec_pack_weight(ptr(w), n, taps, cin, code, ptr(out), stream_ptr()))
+    return out
+
+
+def tdnn_layer_flat(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bias=None, bn_scale=None, bn_shift=None,
+                    relu: bool = True, out: torch.Tensor | None = None, out_dtype: torch.dtype | None = None, cin: int | None = None):
+    """y[r] = bn(relu(sum_j W_j x[r + offsets[j]] + bias)) over a flat (rows, cin) frame matrix; returns (rows, n)."""
+    _require_cuda(x, w_packed, bias, bn_scale, bn_shift, out)
+    lib = _lib.load()
+    x_ld = _rowmajor_2d(x, "x")
+    rows = x.shape[0]
+    cin = x.shape[1] if cin is None else cin
+    if out is None:
+        out = torch.empty((rows, n), dtype=out_dtype or x.dtype, device=x.device)
+    y_ld = _rowmajor_2d(out, "out")
+    if out.shape[0] != rows or out.shape[1] != n:
+        raise ValueError("out must be (rows, n)")
+    if w_packed.dtype != x.dtype:
+        raise ValueError("packed weights and activations must share a dtype")
+    offs = taps_array(offsets)
+    with torch.cuda.device(x.device):
+        check(lib.xvec_tdnn_layer(ptr(x), dtype_code(x.dtype), rows, cin, x_ld, ptr(w_packed), n, offs, len(offsets),
+                                  ptr(bias), ptr(bn_scale), ptr(bn_shift), int(bool(relu)), ptr(out), dtype_code(out.dtype),
+                                  y_ld, rows, stream_ptr()))
+    return out
+
+
+def tdnn_pool_fused(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bias, row_utt: torch.Tensor,
+                    blk_slot_base: torch.Tensor, part: torch.Tensor):
+    """Last TDNN layer with the pooling sums fused into its epilogue; fills part (n_slots, 2, n) float32."""
+    _require_cuda(x, w_packed, bias, row_utt, blk_slot_base, part)
+    lib = _lib.load()
+    x_ld = _rowmajor_2d(x, "x")
+    rows = x.shape[0]
+    if row_utt.dtype != torch.int32 or blk_slot_base.dtype != torch.int32 or part.dtype != torch.float32:
+        raise ValueError("row_utt / blk_slot_base must be int32, part float32")
+    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 127) // 128) * 4 or not part.is_contiguous():
+        raise ValueError("pooling bookkeeping arrays are too small for this frame matrix")
+    offs = taps_array(offsets)
+    with torch.cuda.device(x.device):
+        check(lib.xvec_tdnn_pool_fused(ptr(x), dtype_code(x.dtype), rows, x.shape[1], x_ld, ptr(w_packed), n, offs, len(offsets),
+                                       ptr(bias), ptr(row_utt), ptr(blk_slot_base), ptr(part), rows, stream_ptr()))
+    return part
+
+
+def pool_finalize(part: torch.Tensor, slot_start: torch.Tensor, n_rows: torch.Tensor, p: int, bn_scale=None, bn_shift=None,
+                  out: torch.Tensor | None = None, out_lp: torch.Tensor | None = None):
+    """[mean || unbiased std] per utterance from partial sums; returns float32 (n_utts, 2p)."""
+    _require_cuda(part, slot_start, n_rows, bn_scale, bn_shift, out, out_lp)
+    lib = _lib.load()
+    n_utts = n_rows.numel()
+    if out is None:
+        out = torch.empty((n_utts, 2 * p), dtype=torch.float32, device=part.device)
+    if not out.is_contiguous() or out.shape != (n_utts, 2 * p) or out.dtype != torch.float32:
+        raise ValueError("out must be contiguous float32 (n_utts, 2p)")
+    lp_code, lp_ld = F32, 0
+    if out_lp is not None:
+        lp_ld = _rowmajor_2d(out_lp, "out_lp")
+        lp_code = dtype_code(out_lp.dtype)
+    with torch.cuda.device(part.device):
+        check(lib.xvec_pool_finalize(ptr(part), ptr(slot_start), ptr(n_rows), n_utts, p, ptr(bn_scale), ptr(bn_shift), ptr(out),
+                                     ptr(out_lp), lp_code, lp_ld, stream_ptr()))
+    return out
+
+
+def stats_pool_ragged(x: torch.Tensor, row_start: np.ndarray, n_rows: np.ndarray, out_lp: torch.Tensor | None = None):
+    """Standalone statistics pooling over row ranges of a flat (rows, p) matrix -> float32 (n_utts, 2p)."""
+    _require_cuda(x)
+    lib = _lib.load()
+    ld = _rowmajor_2d(x, "x")
+    p = x.shape[1]
+    row_start = np.asarray(row_start, dtype=np.int64)
+    n_rows = np.asarray(n_rows, dtype=np.int32)
+    if (n_rows < 1).any():
+        raise ValueError("every utterance needs at least one frame to pool")
+    if (row_start < 0).any() or ((row_start + n_rows) > x.shape[0]).any():
+        raise ValueError("row range outside of x")
+    chunks = (n_rows.astype(np.int64) + _lib.POOL_CHUNK - 1) // _lib.POOL_CHUNK
+    slot_start = np.concatenate(([0], np.cumsum(chunks))).astype(np.int32)
+    dev = x.device
+    rs_d = torch.from_numpy(row_start).to(dev)
+    nr_d = torch.from_numpy(n_rows).to(dev)
+    ss_d = torch.from_numpy(slot_start).to(dev)
+    part = torch.empty((int(slot_start[-1]), 2, p), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.xvec_stats_pool_partial(ptr(x), dtype_code(x.dtype), ld, p, ptr(rs_d), ptr(nr_d), ptr(ss_d), len(n_rows),
+                                          int(chunks.max()), ptr(part), stream_ptr()))
+    return pool_finalize(part, ss_d, nr_d, p, out_lp=out_lp)
+
+
+def cast(src: torch.Tensor, dtype: torch.dtype, out: torch.Tensor | None = None) -> torch.Tensor:
+    _require_cuda(src, out)
+    lib = _lib.load()
+    if src.dtype != torch.float32:
+        raise ValueError("cast source must be float32")
+    s_ld = _rowmajor_2d(src, "src")
+    if out is None:
+        out = torch.empty(src.shape, dtype=dtype, device=src.device)
+    d_ld = _rowmajor_2d(out, "out")
+    with torch.cuda.device(src.device):
+        check(lib.xvec_cast(ptr(src), s_ld, ptr(out), dtype_code(out.dtype), d_ld, src.shape[0], src.shape[1], stream_ptr()))
+    return out
+
+
+def cosine_trials(xvecs: torch.Tensor, enrol: torch.Tensor, test: torch.Tensor) -> torch.Tensor:
+    """Cosine score of every (enrol, test) index pair; float32 (n_trials)."""
+    _require_cuda(xvecs, enrol, test)
+    lib = _lib.load()
+    if xvecs.dtype != torch.float32 or enrol.dtype != torch.int32 or test.dtype != torch.int32:
+        raise ValueError("xvecs must be float32, trial indices int32")
+    ld = _rowmajor_2d(xvecs, "xvecs")
+    n = enrol.numel()
+    if test.numel() != n:
+        raise ValueError("enrol and test must have the same length")
+    out = torch.empty(n, dtype=torch.float32, device=xvecs.device)
+    with torch.cuda.device(xvecs.device):
+        check(lib.xvec_cosine_trials(ptr(xvecs), ld, xvecs.shape[1], ptr(enrol.contiguous()), ptr(test.contiguous()), n, ptr(out),
+                                     stream_ptr()))
+    return out

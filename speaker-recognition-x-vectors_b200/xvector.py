@@ -1,0 +1,206 @@
+"""XVectorModel — the extraction surface of the reference's main.XVectorModel (main.py:23-94) on B200.
+
+Same constructor keywords, same sub-module names and state_dict keys (so a reference checkpoint's
+``ckpt['state_dict']`` loads with load_state_dict), same ``forward`` / ``extract_x_vec`` / ``stat_pool`` /
+``test_step`` semantics in eval mode.  The Lightning trainer, dataset and optimiser are out of scope.
+
+Pipeline of extract_x_vec on one flat frame matrix (rows = sum of utterance lengths):
+    TDNN1..4  xvec_tdnn_layer        tcgen05 GEMM, TMA-shifted frame windows, bias+ReLU+BN epilogue
+    TDNN5     xvec_tdnn_pool_fused   same GEMM, epilogue = per-utterance column sums (activation never stored)
+    pooling   xvec_pool_finalize     fixed-order fp64 reduction -> [mean || std], BN5 folded through
+    segment6/7  xvec_tdnn_layer (taps = 1)
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layout import FrameLayout, build_layout
+from .tdnn_layer import TdnnLayer, _aligned_rows, tap_offsets
+
+PRECISIONS = {"tf32": torch.float32, "fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+class _Plan:
+    """Device-side bookkeeping + scratch for one batch layout (reused across calls with the same lengths)."""
+
+    def __init__(self, layout: FrameLayout, device, act_dtype, widths, pool_dim):
+        self.layout = layout
+        self.row_utt = torch.from_numpy(layout.row_utt).to(device)
+        self.blk_slot_base = torch.from_numpy(layout.blk_slot_base).to(device)
+        self.utt_slot_start = torch.from_numpy(layout.utt_slot_start).to(device)
+        self.n_pool = torch.from_numpy(layout.n_pool).to(device)
+        per16 = 16 // torch.empty((), dtype=act_dtype).element_size()
+        ld = (max(widths) + per16 - 1) // per16 * per16
+        self.act = [torch.empty((layout.rows, ld), dtype=act_dtype, device=device) for _ in range(2)]
+        self.part = torch.empty((layout.n_slots, 2, pool_dim), dtype=torch.float32, device=device)
+        self.pooled = torch.empty((layout.n_utts, 2 * pool_dim), dtype=torch.float32, device=device)
+        self.pooled_lp = (torch.empty((layout.n_utts, 2 * pool_dim), dtype=act_dtype, device=device)
+                          if act_dtype != torch.float32 else None)
+
+
+class XVectorModel(nn.Module):
+    def __init__(self, input_size=24, hidden_size=512, num_classes=1211, x_vector_size=512, x_vec_extract_layer=6,
+                 batch_size=512, learning_rate=0.001, batch_norm=True, dropout_p=0.0, augmentations_per_sample=2,
+                 data_folder_path="data", precision="tf32"):
+        super().__init__()
+        self.time_context_layers = nn.Sequential(
+            TdnnLayer(input_size=input_size, output_size=hidden_size, context=[-2, -1, 0, 1, 2], batch_norm=batch_norm, dropout_p=dropout_p),
+            TdnnLayer(input_size=hidden_size, output_size=hidden_size, context=[-2, 0, 2], batch_norm=batch_norm, dropout_p=dropout_p),
+            TdnnLayer(input_size=hidden_size, output_size=hidden_size, context=[-3, 0, 3], batch_norm=batch_norm, dropout_p=dropout_p),
+            TdnnLayer(input_size=hidden_size, output_size=hidden_size, batch_norm=batch_norm, dropout_p=dropout_p),
+            TdnnLayer(input_size=hidden_size, output_size=1500, batch_norm=batch_norm, dropout_p=dropout_p),
+        )
+        self.segment_layer6 = nn.Linear(3000, x_vector_size)
+        self.segment_layer7 = nn.Linear(x_vector_size, x_vector_size)
+        self.output = nn.Linear(x_vector_size, num_classes)
+
+        self.x_vec_extract_layer = x_vec_extract_layer
+        self.batch_size = batch_size
+        self.learning_rate = learning_rate
+        self.input_size = input_size
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.precision = precision
+        self._plans: "OrderedDict[tuple, _Plan]" = OrderedDict()
+        self._fc_prep = {}
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def act_dtype(self) -> torch.dtype:
+        return PRECISIONS[self.precision]
+
+    @property
+    def lost_frames(self) -> int:
+        return sum(tap_offsets(l.context)[-1] for l in self.time_context_layers)
+
+    def _device(self):
+        return self.segment_layer6.weight.device
+
+    def _check_eval(self):
+        if self.training:
+            raise RuntimeError("xvec_b200.XVectorModel implements the eval-mode extraction path only; call .eval() first")
+
+    def _plan_for(self, lengths) -> _Plan:
+        lengths = np.asarray(lengths, dtype=np.int64)
+        dev = self._device()
+        key = (lengths.tobytes(), str(dev), self.precision)
+        plan = self._plans.get(key)
+        if plan is None:
+            layers = list(self.time_context_layers)
+            widths = [l.output_size for l in layers[:-1]]
+            plan = _Plan(build_layout(lengths, self.lost_frames), dev, self.act_dtype, widths, layers[-1].output_size)
+            self._plans[key] = plan
+            while len(self._plans) > 8:
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
+        return plan
+
+    def _fc(self, lin: nn.Linear, dtype):
+        fp = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr() if lin.bias is not None else 0,
+              lin.bias._version if lin.bias is not None else 0, str(lin.weight.device))
+        hit = self._fc_prep.get((id(lin), dtype))
+        if hit is not None and hit[0] == fp:
+            return hit[1]
+        w = ops.pack_weight(lin.weight, 1, lin.in_features, dtype)
+        b = None if lin.bias is None else lin.bias.detach().float().contiguous()
+        self._fc_prep[(id(lin), dtype)] = (fp, (w, b))
+        return w, b
+
+    def _linear(self, lin: nn.Linear, x2d: torch.Tensor, relu: bool, out_dtype) -> torch.Tensor:
+        w, b = self._fc(lin, x2d.dtype)
+        return ops.tdnn_layer_flat(x2d, w, lin.out_features, [0], b, None, None, relu=relu, out_dtype=out_dtype, cin=lin.in_features)
+
+    # ------------------------------------------------------------------ the hot path
+    def pooled_stats_flat(self, flat_x: torch.Tensor, lengths) -> "tuple[torch.Tensor, torch.Tensor | None]":
+        """TDNN stack + statistics pooling over a flat (rows, input_size) float32 frame matrix.
+        Returns (pooled float32 (U, 3000), same in the activation dtype or None)."""
+        self._check_eval()
+        if not flat_x.is_cuda:
+            raise ValueError("xvec_b200 has no CPU path: move the input (and the model) to a CUDA device")
+        if flat_x.dim() != 2 or flat_x.shape[1] != self.input_size:
+            raise ValueError(f"expected a flat (rows, {self.input_size}) frame matrix")
+        plan = self._plan_for(lengths)
+        if plan.layout.rows != flat_x.shape[0]:
+            raise ValueError("sum(lengths) does not match the number of rows")
+        layers = list(self.time_context_layers)
+        if flat_x.dtype != torch.float32:
+            flat_x = flat_x.float()
+        h = _aligned_rows(flat_x)  # layer 1 always reads float32 frames (TF32 math): no cast pass over the input
+        for i, layer in enumerate(layers[:-1]):
+            out = plan.act[i & 1][:, : layer.output_size]
+            h = layer.forward_flat(h, out=out)
+        last = layers[-1]
+        last._check_eval()
+        w, bias, scale, shift = last.prepared(h.dtype)
+        ops.tdnn_pool_fused(h, w, last.output_size, tap_offsets(last.context), bias, plan.row_utt, plan.blk_slot_base, plan.part)
+        ops.pool_finalize(plan.part, plan.utt_slot_start, plan.n_pool, last.output_size, scale, shift, out=plan.pooled,
+                          out_lp=plan.pooled_lp)
+        return plan.pooled, plan.pooled_lp
+
+    def _head(self, pooled, pooled_lp, layer) -> torch.Tensor:
+        a = pooled if pooled_lp is None else pooled_lp
+        if layer == 7:  # main.py:88-90
+            h6 = self._linear(self.segment_layer6, a, relu=True, out_dtype=a.dtype)
+            return self._linear(self.segment_layer7, h6, relu=False, out_dtype=torch.float32)
+        return self._linear(self.segment_layer6, a, relu=False, out_dtype=torch.float32)  # 6 and "anything else" (main.py:86-87,91-92)
+
+    def extract_x_vec_flat(self, flat_x: torch.Tensor, lengths) -> torch.Tensor:
+        """Ragged extraction: flat (sum(lengths), input_size) frames -> float32 (len(lengths), x_vector_size)."""
+        pooled, pooled_lp = self.pooled_stats_flat(flat_x, lengths)
+        return self._head(pooled, pooled_lp, self.x_vec_extract_layer)
+
+    # ------------------------------------------------------------------ reference surface
+    def extract_x_vec(self, x: torch.Tensor) -> torch.Tensor:
+        """main.py:81-94.  x: (B, T, input_size) CUDA tensor -> (B, x_vector_size) float32, the pre-ReLU affine
+        output of segment_layer6 (x_vec_extract_layer 6 / other) or segment_layer7 (7)."""
+        if x.dim() != 3:
+            raise ValueError(f"expected (B, T, {self.input_size}), got {tuple(x.shape)}")
+        B, T, C = x.shape
+        return self.extract_x_vec_flat(x.reshape(B * T, C), [T] * B)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """main.py:66-75 in eval mode: logits (B, num_classes)."""
+        if x.dim() != 3:
+            raise ValueError(f"expected (B, T, {self.input_size}), got {tuple(x.shape)}")
+        B, T, C = x.shape
+        pooled, pooled_lp = self.pooled_stats_flat(x.reshape(B * T, C), [T] * B)
+        a = pooled if pooled_lp is None else pooled_lp
+        h = self._linear(self.segment_layer6, a, relu=True, out_dtype=a.dtype)
+        h = self._linear(self.segment_layer7, h, relu=True, out_dtype=a.dtype)
+        return self._linear(self.output, h, relu=False, out_dtype=torch.float32)
+
+    def stat_pool(self, x: torch.Tensor) -> torch.Tensor:
+        """main.py:59-63: (B, T', P) -> (B, 2P) = [mean over time || unbiased std over time] (standalone HBM-bound kernel)."""
+        if x.dim() != 3:
+            raise ValueError("expected (B, T', P)")
+        if not x.is_cuda:
+            raise ValueError("xvec_b200 has no CPU path: move the input to a CUDA device")
+        B, T, P = x.shape
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        if x.stride(2) != 1 or x.stride(0) != T * x.stride(1) or P % 4 or x.stride(1) % 4 or x.data_ptr() % 16:
+            x = x.contiguous()
+            if P % 4:
+                raise ValueError("stat_pool needs a channel count that is a multiple of 4")
+        ld = x.stride(1)
+        flat = torch.as_strided(x, (B * T, P), (ld, 1))
+        return ops.stats_pool_ragged(flat, np.arange(B, dtype=np.int64) * T, np.full(B, T, dtype=np.int32))
+
+    def test_step(self, batch, batch_index=0):
+        """main.py:135-138 — the extraction step: (samples, labels, ids) -> [(x_vecs, labels, ids)]."""
+        samples, labels, ids = batch
+        x_vecs = self.extract_x_vec(samples.float())
+        return [(x_vecs, labels, ids)]
+
+    def load_reference_checkpoint(self, path: str, map_location="cpu"):
+        """Load the 'state_dict' of a Lightning checkpoint written by the reference (main.py:198,213)."""
+        ckpt = torch.load(path, map_location=map_location, weights_only=False)
+        sd = ckpt.get("state_dict", ckpt)
+        own = set(self.state_dict().keys())
+        return self.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)

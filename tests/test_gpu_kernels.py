@@ -1,0 +1,174 @@
+"""Kernel-level parity on a B200: every C-ABI entry point against the oracle / a plain torch fp32 statement of the op.
+
+Tolerances (north_star): TF32 path max-abs error <= 1e-3 relative to the norm of the reference row;
+bf16 path cosine >= 0.9999 per row.  Integer / layout logic is exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def xb():
+    import xvec_b200
+    assert xvec_b200._lib.load().xvec_device_check() == 0, xvec_b200._lib.load().xvec_last_error()
+    return xvec_b200
+
+
+def _ref_layer(x2d, W, b, offs, scale=None, shift=None, relu=True):
+    """fp64 statement on the flat matrix: y[r] = bn(relu(sum_j W_j x[r+off_j] + b)), rows past the end read zero."""
+    rows, cin = x2d.shape
+    xp = torch.cat([x2d.double(), torch.zeros(max(offs) + 1, cin, dtype=torch.float64)], 0)
+    u = torch.cat([xp[o:o + rows] for o in offs], 1)
+    y = u @ W.double().t() + (b.double() if b is not None else 0)
+    if relu:
+        y = y.clamp_min(0)
+    if scale is not None:
+        y = y * scale.double() + shift.double()
+    return y
+
+
+def _check(got, ref, dtype):
+    got = got.double().cpu()
+    ref = ref.cpu()
+    assert torch.isfinite(got).all()
+    if dtype == torch.float32:
+        err = (got - ref).abs().max(dim=1).values / ref.norm(dim=1).clamp_min(1e-6)
+        assert err.max().item() < 1e-3, err.max().item()
+    else:
+        cos = torch.nn.functional.cosine_similarity(got, ref, dim=1)
+        assert cos.min().item() > 0.9999, cos.min().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,cin,n,offs", [
+    (300, 512, 512, [0]),            # plain k=1 GEMM (TDNN4)
+    (1000, 512, 512, [0, 2, 4]),     # dilated taps (TDNN2)
+    (777, 512, 512, [0, 3, 6]),      # TDNN3, ragged tile edge
+    (515, 24, 512, [0, 1, 2, 3, 4]), # TDNN1: Cin smaller than one K chunk (zero-filled by TMA)
+    (260, 512, 1500, [0]),           # TDNN5 shape, N not a multiple of the tile
+    (129, 40, 96, [0, 3, 6]),        # odd sizes
+    (64, 3000, 512, [0]),            # segment6: long K, few rows
+])
+def test_tdnn_layer_matches_reference(xb, dtype, rows, cin, n, offs):
+    if dtype == torch.bfloat16 and cin % 8:
+        pytest.skip("bf16 rows must be 16-byte aligned")
+    g = torch.Generator().manual_seed(rows * 7 + cin)
+    x = torch.randn(rows, cin, generator=g)
+    W = torch.randn(n, cin * len(offs), generator=g) / (cin * len(offs)) ** 0.5
+    b = torch.randn(n, generator=g) * 0.1
+    scale = 1 + 0.5 * torch.randn(n, generator=g)
+    shift = 0.5 * torch.randn(n, generator=g)
+    xd = x.cuda().to(dtype)
+    wp = xb.ops.pack_weight(W.cuda(), len(offs), cin, dtype)
+    assert wp.shape == (-(-n // 256) * 256, len(offs) * (-(-cin // (32 if dtype == torch.float32 else 64))) * (32 if dtype == torch.float32 else 64))
+    y = xb.ops.tdnn_layer_flat(xd, wp, n, offs, b.cuda(), scale.cuda(), shift.cuda(), relu=True)
+    torch.cuda.synchronize()
+    assert y.shape == (rows, n) and y.dtype == dtype
+    ref = _ref_layer(xd.float().cpu(), W.to(dtype).float() if dtype == torch.bfloat16 else W, b, offs, scale, shift)
+    _check(y, ref, dtype)
+    # no relu / no bn / fp32 output from any input type
+    y2 = xb.ops.tdnn_layer_flat(xd, wp, n, offs, b.cuda(), None, None, relu=False, out_dtype=torch.float32)
+    ref2 = _ref_layer(xd.float().cpu(), W.to(dtype).float() if dtype == torch.bfloat16 else W, b, offs, relu=False)
+    _check(y2, ref2, dtype)
+    assert xb._lib.load().xvec_watchdog_code() == 0
+
+
+def test_tdnn_layer_many_tiles_exercises_pipeline_wraparound(xb):
+    # > 148*2 tiles per CTA round and > 4 stages: phases of every barrier wrap several times
+    rows, cin, n, offs = 148 * 128 * 3 + 77, 512, 512, [0, 2, 4]
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(rows, cin, generator=g).cuda().bfloat16()
+    W = torch.randn(n, cin * 3, generator=g) / (cin * 3) ** 0.5
+    wp = xb.ops.pack_weight(W.cuda(), 3, cin, torch.bfloat16)
+    y = xb.ops.tdnn_layer_flat(x, wp, n, offs, None, None, None, relu=False, out_dtype=torch.float32)
+    xp = torch.cat([x.float(), torch.zeros(8, cin, device="cuda")], 0)
+    ref = torch.cat([xp[o:o + rows] for o in offs], 1) @ W.cuda().bfloat16().float().t()
+    err = (y - ref).abs().max().item()
+    assert err < 2e-2 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stats_pool_standalone(xb, dtype):
+    g = torch.Generator().manual_seed(5)
+    lens = [1, 2, 17, 128, 129, 300, 1000]
+    starts = np.concatenate(([0], np.cumsum(lens)[:-1]))
+    x = (torch.randn(sum(lens), 1500, generator=g) + 0.7).cuda().to(dtype)
+    out = xb.ops.stats_pool_ragged(x, starts, np.asarray(lens))
+    for u, (s, l) in enumerate(zip(starts, lens)):
+        seg = x[s:s + l].double()
+        assert torch.allclose(out[u, :1500].double(), seg.mean(0), atol=2e-5, rtol=1e-5)
+        if l > 1:
+            assert torch.allclose(out[u, 1500:].double(), seg.std(0), atol=5e-5, rtol=1e-4)
+        else:
+            assert torch.isnan(out[u, 1500:]).all()   # torch.std of one frame is NaN (main.py:61)
+
+
+def test_stat_pool_module_surface(xb, state_dict):
+    m = xb.XVectorModel().cuda().eval()
+    x = torch.randn(5, 61, 1500, device="cuda")
+    ref = torch.cat((x.mean(1), x.std(1)), 1)
+    assert torch.allclose(m.stat_pool(x), ref, atol=5e-5, rtol=1e-4)
+    xs = x[:, :40]  # strided view like a TdnnLayer output
+    assert torch.allclose(m.stat_pool(xs), torch.cat((xs.mean(1), xs.std(1)), 1), atol=5e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_tdnn5_pool_matches_unfused(xb, dtype):
+    """TDNN5 + pooling fused (activation never stored) == TDNN5 store kernel + masked pooling, on a ragged batch
+    whose utterance boundaries fall inside 32-row blocks and 128-row tiles."""
+    lens = np.asarray([15, 16, 47, 300, 33, 129, 640, 20])
+    lay = xb.build_layout(lens)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(lay.rows, 512, generator=g).cuda().to(dtype)
+    W = torch.randn(1500, 512, generator=g) / 512 ** 0.5
+    b = torch.randn(1500, generator=g) * 0.2
+    scale = (1 + 0.5 * torch.randn(1500, generator=g)).cuda()
+    shift = (0.5 * torch.randn(1500, generator=g)).cuda()
+    wp = xb.ops.pack_weight(W.cuda(), 1, 512, dtype)
+    part = torch.full((lay.n_slots, 2, 1500), float("nan"), device="cuda")
+    xb.ops.tdnn_pool_fused(x, wp, 1500, [0], b.cuda(), torch.from_numpy(lay.row_utt).cuda(),
+                           torch.from_numpy(lay.blk_slot_base).cuda(), part)
+    assert torch.isfinite(part).all()       # every slot written exactly by the kernel
+    pooled = xb.ops.pool_finalize(part, torch.from_numpy(lay.utt_slot_start).cuda(), torch.from_numpy(lay.n_pool).cuda(),
+                                  1500, scale, shift)
+    r = xb.ops.tdnn_layer_flat(x, wp, 1500, [0], b.cuda(), None, None, relu=True, out_dtype=torch.float32).double()
+    z = r * scale.double() + shift.double()
+    for u in range(len(lens)):
+        seg = z[lay.starts[u]: lay.starts[u] + lay.n_pool[u]]
+        assert torch.allclose(pooled[u, :1500].double(), seg.mean(0), atol=1e-4, rtol=1e-4), u
+        if lay.n_pool[u] > 1:
+            assert torch.allclose(pooled[u, 1500:].double(), seg.std(0), atol=2e-4, rtol=2e-4), u
+        else:
+            assert torch.isnan(pooled[u, 1500:]).all()
+    # run-to-run bit reproducibility (fixed-order reduction, no atomics)
+    part2 = torch.empty_like(part)
+    xb.ops.tdnn_pool_fused(x, wp, 1500, [0], b.cuda(), torch.from_numpy(lay.row_utt).cuda(),
+                           torch.from_numpy(lay.blk_slot_base).cuda(), part2)
+    assert torch.equal(part, part2)
+
+
+def test_cast_and_cosine(xb):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(100, 24, generator=g).cuda()
+    assert torch.equal(xb.ops.cast(x, torch.bfloat16), x.bfloat16())
+    xv = torch.randn(50, 512, generator=g).cuda()
+    e = torch.randint(0, 50, (1000,), generator=g).int().cuda()
+    t = torch.randint(0, 50, (1000,), generator=g).int().cuda()
+    ref = torch.nn.functional.cosine_similarity(xv[e.long()].double(), xv[t.long()].double(), dim=1)
+    assert (xb.ops.cosine_trials(xv, e, t).double() - ref).abs().max().item() < 1e-5
+
+
+def test_argument_errors(xb):
+    x = torch.randn(64, 512, device="cuda")
+    wp = xb.ops.pack_weight(torch.randn(512, 512, device="cuda"), 1, 512, torch.float32)
+    with pytest.raises(ValueError):
+        xb.ops.tdnn_layer_flat(x.cpu(), wp, 512, [0])              # no CPU path
+    with pytest.raises(xb._lib.XvecError):
+        xb.ops.tdnn_layer_flat(x, wp, 512, [0] * 9)                # too many taps
+    with pytest.raises(xb._lib.XvecError):
+        xb.ops.tdnn_layer_flat(x[:, 1:], wp, 511, [0], cin=511)    # misaligned rows
+    with pytest.raises(ValueError):
+        xb.TdnnLayer(24, 32, [-1, 0, 2]).cuda().eval()(torch.randn(1, 30, 24, device="cuda"))

@@ -1,0 +1,140 @@
+"""Model-level parity on a B200 through the reference's module surface: TdnnLayer.forward, XVectorModel.extract_x_vec /
+forward / stat_pool / test_step against the CPU oracle and the committed golden vectors of the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import xvector_oracle as ox
+
+pytestmark = pytest.mark.gpu
+
+TOL_TF32 = 1e-3       # max-abs error relative to the norm of the reference embedding (north_star)
+MIN_COS_BF16 = 0.9999
+
+
+def _model(xb, sd, precision, layer=6):
+    m = xb.XVectorModel(x_vec_extract_layer=layer, precision=precision)
+    assert not m.load_state_dict(sd, strict=True).missing_keys
+    return m.cuda().eval()
+
+
+def _assert_parity(got, ref, precision):
+    got = np.asarray(got.detach().float().cpu(), np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert got.shape == ref.shape and np.isfinite(got).all()
+    rel = np.abs(got - ref).max(1) / np.linalg.norm(ref, axis=1)
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    if precision == "tf32":
+        assert rel.max() < TOL_TF32, rel.max()
+    assert cos.min() > MIN_COS_BF16, cos.min()
+    return rel.max(), cos.min()
+
+
+@pytest.fixture(scope="module")
+def xb():
+    import xvec_b200
+    return xvec_b200
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("tag", ["b4_t299", "b8_t300", "b3_t16"])
+def test_extract_matches_reference_golden(xb, golden, state_dict, precision, tag):
+    b, t, seed = golden[tag + "_shape_seed"].tolist()
+    x = ox.synth_mfcc(b, t, seed=seed).cuda()
+    for layer, key in ((6, "_l6"), (7, "_l7"), (3, "_l3")):
+        m = _model(xb, state_dict, precision, layer)
+        _assert_parity(m.extract_x_vec(x), golden[tag + key], precision)
+    m = _model(xb, state_dict, precision)
+    _assert_parity(m(x), golden[tag + "_fwd"], precision)
+    out = m.test_step((x.double(), torch.arange(b), [f"id{i}" for i in range(b)]))
+    assert torch.equal(out[0][0], m.extract_x_vec(x)) and out[0][2][0] == "id0"
+
+
+def test_single_pooled_frame_is_nan_like_reference(xb, golden, state_dict):
+    b, t, seed = golden["b2_t15_shape_seed"].tolist()
+    got = _model(xb, state_dict, "tf32").extract_x_vec(ox.synth_mfcc(b, t, seed=seed).cuda())
+    assert torch.isnan(got).all() and np.isnan(golden["b2_t15_l6"]).all()
+    with pytest.raises(ValueError):
+        _model(xb, state_dict, "tf32").extract_x_vec(torch.randn(2, 14, 24, device="cuda"))
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_layer_activations_match_reference_golden(xb, golden, state_dict, precision):
+    m = _model(xb, state_dict, precision)
+    h = ox.synth_mfcc(2, 40, seed=21).cuda()
+    if precision == "bf16":
+        h1 = m.time_context_layers[0](h)           # fp32 in (TF32 math)
+        hs = [h1]
+        cur = h1.bfloat16()
+        for layer in list(m.time_context_layers)[1:]:
+            cur = layer(cur.contiguous())
+            hs.append(cur)
+    else:
+        hs, cur = [], h
+        for layer in m.time_context_layers:
+            cur = layer(cur.contiguous())
+            hs.append(cur)
+    for i, a in enumerate(hs):
+        ref = golden[f"act_l{i + 1}"]
+        assert tuple(a.shape) == ref.shape
+        got = a.float().cpu().numpy().reshape(-1, ref.shape[-1])
+        r = ref.reshape(-1, ref.shape[-1])
+        rel = np.abs(got - r).max(1) / np.linalg.norm(r, axis=1)
+        assert rel.max() < (2e-3 if precision == "tf32" else 3e-2), (i, rel.max())
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_ragged_matches_per_utterance_reference(xb, golden, state_dict, precision):
+    lens = golden["ragged_lengths"]
+    utts = ox.synth_ragged(lens, seed=77)
+    m = _model(xb, state_dict, precision)
+    got = m.extract_x_vec_flat(torch.cat(utts).cuda(), lens)
+    _assert_parity(got, golden["ragged_l6"], precision)
+    # permuting the utterances permutes the embeddings bit-for-bit-tolerantly (no cross-utterance leakage)
+    perm = np.random.default_rng(0).permutation(len(lens))
+    got_p = m.extract_x_vec_flat(torch.cat([utts[i] for i in perm]).cuda(), lens[perm])
+    assert torch.allclose(got_p, got[perm], atol=1e-5 if precision == "tf32" else 5e-3)
+
+
+def test_layer_without_bn_matches_reference_golden(xb, golden):
+    lay = xb.TdnnLayer(input_size=40, output_size=96, context=[-3, 0, 3], batch_norm=False)
+    with torch.no_grad():
+        lay.linear.weight.copy_(torch.from_numpy(golden["layer_nobn_w"]))
+        lay.linear.bias.copy_(torch.from_numpy(golden["layer_nobn_b"]))
+    lay = lay.cuda().eval()
+    y = lay(ox.synth_mfcc(3, 50, 40, seed=9).cuda())
+    ref = golden["layer_nobn_y"]
+    assert tuple(y.shape) == ref.shape == (3, 44, 96)
+    assert np.abs(y.cpu().numpy() - ref).max() < 5e-3
+    # parameters changed in place -> packed weights are rebuilt
+    with torch.no_grad():
+        lay.linear.weight.mul_(2.0)
+        lay.linear.bias.mul_(2.0)
+    assert np.abs(lay(ox.synth_mfcc(3, 50, 40, seed=9).cuda()).cpu().numpy() - 2 * ref).max() < 1e-2
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_config1_batch64_against_oracle(xb, state_dict, precision):
+    """BASELINE.json config 1 (64 x 300 x 24, batch 64) — oracle computed here on the host cores."""
+    x = ox.synth_mfcc(64, 300, seed=1234)
+    ref = ox.extract_x_vec_t(state_dict, x, 6).numpy()
+    m = _model(xb, state_dict, precision)
+    rel, cos = _assert_parity(m.extract_x_vec(x.cuda()), ref, precision)
+    # bitwise reproducible from run to run
+    assert torch.equal(m.extract_x_vec(x.cuda()), m.extract_x_vec(x.cuda()))
+
+
+def test_trial_decisions_identical(xb, state_dict):
+    """Cosine trial decisions from GPU embeddings == decisions from oracle embeddings at the oracle's EER threshold."""
+    lens = ox.synth_lengths(120, 100, 400, seed=3)
+    utts = ox.synth_ragged(lens, seed=55)
+    ref = ox.extract_ragged_t(state_dict, utts, 6).numpy()
+    enrol, test, target = ox.synth_trials(120, 3000, n_speakers=12, seed=4)
+    s_ref = ox.cosine_scores_np(ref, enrol, test)
+    _, thr, margin = ox.eer_threshold_np(s_ref, target)
+    for precision in ("tf32", "bf16"):
+        m = _model(xb, state_dict, precision)
+        xv = m.extract_x_vec_flat(torch.cat(utts).cuda(), lens)
+        s = xb.ops.cosine_trials(xv, torch.from_numpy(enrol).int().cuda(), torch.from_numpy(test).int().cuda()).cpu().numpy()
+        assert np.abs(s - s_ref).max() < margin, (precision, np.abs(s - s_ref).max(), margin)
+        assert np.array_equal(s >= thr, s_ref >= thr)
