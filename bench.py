@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the x-vector extraction hot path (BASELINE.json metric: x-vectors/sec & frames/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype bf16|tf32] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU, weak scaling)
+
+A step = one pass of the hot path (TDNN1-5 -> statistics pooling -> segment6) over ONE batch of the workload
+(BASELINE.json configs[1]: 1024 fixed-length 3 s utterances = 4 batches of 256 x 300 x 24 MFCC, cycled).
+  value      utterances/s, device-resident inputs, summed per-step CUDA-event time (L2 flushed between steps)
+  e2e        utterances/s through the public host API (HostExtractor): pinned host MFCCs -> H2D -> kernels -> D2H x-vectors
+  roofline   tcgen05 TDNN kernel: algorithmic FLOPs of its launches / their CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle (port of the reference's fp32 PyTorch path) on this box's host cores, bounded sample
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH, FRAMES, CEPS, N_UTTS = 256, 300, 24, 1024          # BASELINE.json configs[1]
+FLOPS_L = [122_880, 1_572_864, 1_572_864, 524_288, 1_536_000]  # per output frame, SURVEY §8d
+LOST = [4, 8, 14, 14, 14]
+SEG6_FLOPS = 3_072_000
+
+
+def flops_per_utt(t):
+    return sum(f * (t - l) for f, l in zip(FLOPS_L, LOST)) + SEG6_FLOPS
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port of its fp32 PyTorch ops), all host threads."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import xvector_oracle as ox
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = ox.make_state_dict(seed=0)
+    sample = 64  # utterances of the 256-utterance batch per step (bounded CPU sample)
+    x = ox.synth_mfcc(sample, FRAMES, seed=1234)
+    for _ in range(args.warmup):
+        ox.extract_x_vec_t(sd, x, 6)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ox.extract_x_vec_t(sd, x, 6)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "x-vectors/sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_sec": v * FRAMES,
+            "config": {"workload": "c2: 1024 x 3 s utterances (300 x 24 MFCC), batch 256, x_vec_extract_layer 6"},
+            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{sample} of the {BATCH} utterances of a batch per step, oracle/xvector_oracle.extract_x_vec_t (fp32 torch CPU)"},
+            "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def cpu_baseline_leg(budget_s=12.0):
+    import torch
+    from oracle import xvector_oracle as ox
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = ox.make_state_dict(seed=0)
+    x = ox.synth_mfcc(64, FRAMES, seed=1234)  # BASELINE.json configs[0]
+    for _ in range(2):
+        ox.extract_x_vec_t(sd, x, 6)
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 5 or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        ox.extract_x_vec_t(sd, x, 6)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": 64 / med, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"config c1 (64 x 300 x 24, batch 64), median of {len(times)} runs of the oracle port (fp32 torch CPU ops of the reference path)",
+            "frames_per_sec": 64 * FRAMES / med, "gflops": 64 * flops_per_utt(FRAMES) / med / 1e9, "best_utt_s": 64 / times[0]}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import xvec_b200
+    from oracle import xvector_oracle as ox  # only for seeded synthetic weights/inputs and the cpu_baseline leg
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.dtype
+    model = xvec_b200.XVectorModel(precision=precision)
+    model.load_state_dict(ox.make_state_dict(seed=0))
+    model = model.to(dev).eval()
+
+    n_batches = N_UTTS // BATCH
+    x_host = ox.synth_mfcc(N_UTTS, FRAMES, seed=1234 + rank).reshape(n_batches, BATCH * FRAMES, CEPS).pin_memory()
+    x_dev = x_host.to(dev)
+    lengths = [FRAMES] * BATCH
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(i):
+        return model.extract_x_vec_flat(x_dev[i % n_batches], lengths)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: per-step event pairs, L2 flushed in between
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- end to end through the host API (pinned host -> H2D -> kernels -> D2H), double-buffered
+    hx = xvec_b200.HostExtractor(model, n_slots=2)
+    for i in range(3):
+        hx.result(hx.submit(x_host[i % n_batches], lengths))
+    barrier()
+    hx.h2d_bytes = hx.d2h_bytes = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e2e = time.perf_counter()
+    e0.record()
+    tickets = []
+    checksum = 0.0
+    for i in range(args.steps):
+        tickets.append(hx.submit(x_host[i % n_batches], lengths))
+        if len(tickets) == 2:
+            checksum += float(hx.result(tickets.pop(0))[0, 0])
+    while tickets:
+        checksum += float(hx.result(tickets.pop(0))[0, 0])
+    e1.record()
+    barrier()
+    t_e2e = time.perf_counter() - t_e2e
+    clocks = sampler.stop()
+
+    # ---- per-kernel timing of the dominant kernel (separate instrumented pass; not part of the numbers above)
+    layer_ms = instrumented_layer_times(model, x_dev, lengths, n_batches, iters=max(5, min(args.steps, 20)))
+
+    dev_ms_t = torch.tensor([dev_ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dev_ms_t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = dev_ms_t.tolist()
+
+    if rank == 0:
+        peaks = load_peaks()
+        utts = BATCH * args.steps * world
+        value = utts / (dev_ms / 1e3)
+        e2e = utts / (e2e_ms / 1e3)
+        tdnn_ms = sum(layer_ms[f"tdnn{i + 1}"] for i in range(5))
+        tdnn_flops = BATCH * sum(f * (FRAMES - l) for f, l in zip(FLOPS_L, LOST))
+        achieved = tdnn_flops / (tdnn_ms / 1e3) / 1e12
+        peak = peaks["bf16_tflops_sustained"] if precision == "bf16" else peaks["bf16_tflops_sustained"] / 2
+        per_layer = {k: {"ms": round(v, 5)} for k, v in layer_ms.items()}
+        for i in range(5):
+            fl = BATCH * FLOPS_L[i] * (FRAMES - LOST[i])
+            per_layer[f"tdnn{i + 1}"]["tflops"] = round(fl / (layer_ms[f"tdnn{i + 1}"] / 1e3) / 1e12, 2)
+        line = {
+            "metric": "x-vectors/sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if precision == "bf16" else "tf32", "data": "synthetic",
+            "frames_per_sec": value * FRAMES,
+            "config": {"workload": "c2: 1024 x 3 s utterances (300 x 24 MFCC), batch 256 per step and GPU, x_vec_extract_layer 6",
+                       "global_batch": BATCH * world, "frames": FRAMES, "parallelism": f"utterance-sharded x{world}, no data-path collective",
+                       "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pairs)",
+                       "tdnn1": "TF32 math on the float32 MFCCs in both modes"},
+            "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": hx.h2d_bytes // args.steps, "d2h_bytes_per_step": hx.d2h_bytes // args.steps,
+                    "api": "HostExtractor.submit/result (pinned host MFCCs in, pinned host x-vectors out, 2 streams)",
+                    "frames_per_sec": e2e * FRAMES, "checksum": checksum},
+            "gpu_launches": args.steps * 7,
+            "clocks": clocks,
+            "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+            "roofline": {"kernel": "tdnn_gemm_kernel (5 launches/step: TDNN1-4 store epilogue, TDNN5 fused pooling epilogue)",
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops_sustained" + ("" if precision == "bf16" else " / 2 (TF32)"),
+                         "frac_of_burst_peak": achieved / (peaks["bf16_tflops"] if precision == "bf16" else peaks["bf16_tflops"] / 2),
+                         "algorithmic_flops_per_step": tdnn_flops, "ms_per_step": tdnn_ms},
+            "kernels": per_layer,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def instrumented_layer_times(model, x_dev, lengths, n_batches, iters):
+    """CUDA-event time of every launch of one step, averaged over `iters` steps (events on the launching stream)."""
+    import torch
+    import xvec_b200
+    from xvec_b200 import ops
+    from xvec_b200.tdnn_layer import tap_offsets, _aligned_rows
+    names = ["tdnn1", "tdnn2", "tdnn3", "tdnn4", "tdnn5", "pool_finalize", "segment6"]
+    acc = dict.fromkeys(names, 0.0)
+    layers = list(model.time_context_layers)
+    plan = model._plan_for(lengths, 0)
+    for it in range(iters + 2):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        h = _aligned_rows(x_dev[it % n_batches])
+        evs[0].record()
+        for i, layer in enumerate(layers[:-1]):
+            h = layer.forward_flat(h, out=plan.act[i & 1][:, : layer.output_size])
+            evs[i + 1].record()
+        last = layers[-1]
+        w, bias, scale, shift = last.prepared(h.dtype)
+        ops.tdnn_pool_fused(h, w, last.output_size, tap_offsets(last.context), bias, plan.row_utt, plan.blk_slot_base, plan.part)
+        evs[5].record()
+        ops.pool_finalize(plan.part, plan.utt_slot_start, plan.n_pool, last.output_size, scale, shift, out=plan.pooled, out_lp=plan.pooled_lp)
+        evs[6].record()
+        model._head(plan.pooled, plan.pooled_lp, 6)
+        evs[7].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            for k, name in enumerate(names):
+                acc[name] += evs[k].elapsed_time(evs[k + 1])
+    return {k: v / iters for k, v in acc.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
+        import subprocess
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

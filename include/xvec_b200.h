@@ -125,11 +125,12 @@ XVEC_API int xvec_pool_finalize(const float* part_dev, const int32_t* slot_start
 XVEC_API int xvec_cast(const float* src_dev, int64_t src_ld, void* dst_dev, int dst_dtype, int64_t dst_ld, int64_t rows,
               int cols, void* stream);
 
-/* Cosine score of each trial: out[i] = <a,b>/(|a||b|) with a = xvec[enrol[i]], b = xvec[test[i]] (float32 in,
- * float32 out, float32 accumulation).  BASELINE.json config 5; the reference scores with PLDA on the full NxN
- * matrix and picks trial entries afterwards (plda_score_stat.py:59-87). */
-XVEC_API int xvec_cosine_trials(const float* xvec_dev, int64_t ld, int dim, const int32_t* enrol_dev, const int32_t* test_dev,
-                       int64_t n_trials, float* out_dev, void* stream);
+/* Cosine score of each trial: out[i] = <a,b>/(|a||b|) with a = xvec[enrol[i]] - mean, b = xvec[test[i]] - mean
+ * (float32 in, float32 out, float32 accumulation; mean_dev float32 (dim) or NULL for no centring).
+ * BASELINE.json config 5; the reference scores with PLDA on the full NxN matrix and picks trial entries afterwards
+ * (plda_score_stat.py:59-87). */
+XVEC_API int xvec_cosine_trials(const float* xvec_dev, int64_t ld, int dim, const float* mean_dev, const int32_t* enrol_dev,
+                       const int32_t* test_dev, int64_t n_trials, float* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -307,9 +307,25 @@ def synth_trials(n_utts: int, n_trials: int, n_speakers: int = 40, seed: int = 4
     return enrol[perm], test[perm], target[perm]
 
 
-def cosine_scores_np(xvecs: np.ndarray, enrol: np.ndarray, test: np.ndarray) -> np.ndarray:
-    """fp64 cosine score per trial (BASELINE.json config 5; not present in the reference)."""
+def synth_speaker_utts(lengths: Sequence[int], n_speakers: int, n_ceps: int = 24, seed: int = 55, spk_sigma: float = 1.0,
+                       sess_sigma: float = 0.1) -> List[torch.Tensor]:
+    """Ragged synthetic MFCCs with speaker structure: frames ~ N(0,1) + a per-speaker offset (round-robin speakers,
+    matching synth_trials) + a small per-utterance session offset, so cosine trials are meaningful."""
+    g = torch.Generator().manual_seed(seed)
+    spk = torch.randn(n_speakers, n_ceps, generator=g) * spk_sigma
+    out = []
+    for i, l in enumerate(lengths):
+        sess = torch.randn(n_ceps, generator=g) * sess_sigma
+        out.append(torch.randn(int(l), n_ceps, generator=g) + spk[i % n_speakers] + sess)
+    return out
+
+
+def cosine_scores_np(xvecs: np.ndarray, enrol: np.ndarray, test: np.ndarray, center: bool = False) -> np.ndarray:
+    """fp64 cosine score per trial (BASELINE.json config 5; not present in the reference).  center=True subtracts the
+    mean x-vector of the set first (random-init embeddings share a large common component)."""
     x = np.asarray(xvecs, dtype=np.float64)
+    if center:
+        x = x - x.mean(0, keepdims=True)
     x = x / np.linalg.norm(x, axis=1, keepdims=True)
     return np.einsum("ij,ij->i", x[enrol], x[test])
 

@@ -8,8 +8,9 @@ from . import _lib, layout, ops  # noqa: F401
 from .layout import build_layout, bucket_batches, lpt_partition  # noqa: F401
 from .tdnn_layer import TdnnLayer, get_time_context, tap_offsets  # noqa: F401
 from .xvector import XVectorModel  # noqa: F401
+from .extractor import HostExtractor  # noqa: F401
 
 TDNN = TdnnLayer  # BASELINE.json's north_star calls the layer "TDNN"
 
 __all__ = ["TdnnLayer", "TDNN", "XVectorModel", "get_time_context", "tap_offsets", "build_layout", "bucket_batches",
-           "lpt_partition", "ops", "layout"]
+           "lpt_partition", "ops", "layout", "HostExtractor"]

@@ -147,8 +147,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int n, int taps,
 // ------------------------------------------------------------------------------------------------ cosine trials
 // one warp per trial
 __global__ void __launch_bounds__(256)
-cosine_trials_kernel(const float* __restrict__ xv, long long ld, int dim, const int* __restrict__ enrol, const int* __restrict__ test,
-                     long long n_trials, float* __restrict__ out) {
+cosine_trials_kernel(const float* __restrict__ xv, long long ld, int dim, const float* __restrict__ mean, const int* __restrict__ enrol,
+                     const int* __restrict__ test, long long n_trials, float* __restrict__ out) {
   const long long t = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t >= n_trials) return;
@@ -156,7 +156,8 @@ cosine_trials_kernel(const float* __restrict__ xv, long long ld, int dim, const 
   const float* b = xv + static_cast<long long>(test[t]) * ld;
   float ab = 0.f, aa = 0.f, bb = 0.f;
   for (int i = lane; i < dim; i += 32) {
-    const float x = a[i], y = b[i];
+    const float mu = mean ? mean[i] : 0.f;
+    const float x = a[i] - mu, y = b[i] - mu;
     ab = fmaf(x, y, ab);
     aa = fmaf(x, x, aa);
     bb = fmaf(y, y, bb);
@@ -254,15 +255,15 @@ int xvec_pack_weight(const float* w_dev, int n, int taps, int cin, int dtype, vo
   return check_launch("pack_weight_kernel");
 }
 
-int xvec_cosine_trials(const float* xvec_dev, int64_t ld, int dim, const int32_t* enrol_dev, const int32_t* test_dev, int64_t n_trials,
-                       float* out_dev, void* stream) {
+int xvec_cosine_trials(const float* xvec_dev, int64_t ld, int dim, const float* mean_dev, const int32_t* enrol_dev,
+                       const int32_t* test_dev, int64_t n_trials, float* out_dev, void* stream) {
   int rc = device_check();
   if (rc) return rc;
   if (!xvec_dev || !enrol_dev || !test_dev || !out_dev) return set_error(XVEC_E_ARG, "null pointer argument");
   if (dim <= 0 || ld < dim || n_trials <= 0) return set_error(XVEC_E_ARG, "bad shape");
   const long long blocks = (n_trials * 32 + 255) / 256;
-  cosine_trials_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(xvec_dev, ld, dim, enrol_dev, test_dev,
-                                                                                                   n_trials, out_dev);
+  cosine_trials_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(xvec_dev, ld, dim, mean_dev, enrol_dev,
+                                                                                                   test_dev, n_trials, out_dev);
   return check_launch("cosine_trials_kernel");
 }
 

@@ -1,0 +1,104 @@
+"""Host-facing extraction: pinned host MFCC buffers in, host x-vectors out — the call a user of the reference's
+test_step/test_epoch_end (main.py:135-146) makes, minus the per-utterance .cpu() round trips.
+
+Each of the `n_slots` slots owns a CUDA stream, a device staging buffer, model scratch and a pinned result buffer, so
+the host->device copy of batch i+1 overlaps the kernels of batch i and the device->host copy of batch i-1.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from .layout import bucket_batches
+
+
+@dataclass
+class _Slot:
+    stream: torch.cuda.Stream
+    done: torch.cuda.Event
+    x_dev: torch.Tensor | None = None
+    out_host: torch.Tensor | None = None
+    n_out: int = 0
+    busy: bool = False
+
+
+class HostExtractor:
+    def __init__(self, model, n_slots: int = 2):
+        self.model = model
+        self.device = model._device()
+        if self.device.type != "cuda":
+            raise ValueError("xvec_b200 has no CPU path: move the model to a CUDA device first")
+        with torch.cuda.device(self.device):
+            self.slots = [_Slot(torch.cuda.Stream(), torch.cuda.Event()) for _ in range(n_slots)]
+        self._next = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def submit(self, x_host: torch.Tensor, lengths) -> int:
+        """Enqueue one batch: x_host is a float32 host tensor (rows, C) or (B, T, C), ideally pinned.  Returns a ticket."""
+        if x_host.is_cuda:
+            raise ValueError("HostExtractor.submit takes host tensors; call model.extract_x_vec for device tensors")
+        if x_host.dim() == 3:
+            x_host = x_host.reshape(-1, x_host.shape[-1])
+        if x_host.dtype != torch.float32:
+            x_host = x_host.float()  # main.py:137 samples.float()
+        i = self._next
+        self._next = (self._next + 1) % len(self.slots)
+        sl = self.slots[i]
+        if sl.busy:
+            sl.done.synchronize()
+        rows, c = x_host.shape
+        n_utts = len(lengths)
+        dim = (self.model.segment_layer7 if self.model.x_vec_extract_layer == 7 else self.model.segment_layer6).out_features
+        with torch.cuda.device(self.device), torch.cuda.stream(sl.stream):
+            if sl.x_dev is None or sl.x_dev.shape[0] < rows or sl.x_dev.shape[1] != c:
+                sl.x_dev = torch.empty((rows, c), dtype=torch.float32, device=self.device)
+            if sl.out_host is None or sl.out_host.shape[0] < n_utts or sl.out_host.shape[1] != dim:
+                sl.out_host = torch.empty((n_utts, dim), dtype=torch.float32, pin_memory=True)
+            xd = sl.x_dev[:rows]
+            xd.copy_(x_host, non_blocking=True)
+            xv = self.model.extract_x_vec_flat(xd, lengths, slot=i)
+            sl.out_host[:n_utts].copy_(xv, non_blocking=True)
+            sl.done.record(sl.stream)
+        sl.n_out = n_utts
+        sl.busy = True
+        self.h2d_bytes += rows * c * 4
+        self.d2h_bytes += n_utts * dim * 4
+        return i
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Host float32 (n_utts, dim) view of the slot's pinned result buffer (valid until the slot is reused)."""
+        sl = self.slots[ticket]
+        sl.done.synchronize()
+        sl.busy = False
+        return sl.out_host[: sl.n_out]
+
+    def extract_all(self, utts, max_frames: int = 1 << 17, max_utts: int = 1024) -> np.ndarray:
+        """Extract a whole (ragged) list of host (T_i, C) float32 tensors: length-bucketed batches, double-buffered.
+        Returns float64 (N, dim) in the original order, the dtype test_epoch_end stores (main.py:145)."""
+        lengths = np.asarray([int(u.shape[0]) for u in utts], dtype=np.int64)
+        out = None
+        pending = []
+
+        def drain(k):
+            nonlocal out
+            while len(pending) > k:
+                ticket, idx = pending.pop(0)
+                r = self.result(ticket).numpy()
+                if out is None:
+                    out = np.empty((len(utts), r.shape[1]), dtype=np.float64)
+                out[idx] = r
+
+        stage = [None] * len(self.slots)
+        for idx in bucket_batches(lengths, max_frames, max_utts):
+            drain(len(self.slots) - 1)
+            rows = int(lengths[idx].sum())
+            k = self._next
+            if stage[k] is None or stage[k].shape[0] < rows:
+                stage[k] = torch.empty((max(rows, max_frames), utts[0].shape[1]), dtype=torch.float32, pin_memory=True)
+            torch.cat([utts[i] for i in idx], out=stage[k][:rows])
+            pending.append((self.submit(stage[k][:rows], lengths[idx]), idx))
+        drain(0)
+        return out

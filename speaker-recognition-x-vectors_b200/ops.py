@@ -138,8 +138,9 @@ def cast(src: torch.Tensor, dtype: torch.dtype, out: torch.Tensor | None = None)
     return out
 
 
-def cosine_trials(xvecs: torch.Tensor, enrol: torch.Tensor, test: torch.Tensor) -> torch.Tensor:
-    """Cosine score of every (enrol, test) index pair; float32 (n_trials)."""
+def cosine_trials(xvecs: torch.Tensor, enrol: torch.Tensor, test: torch.Tensor, center: bool = False) -> torch.Tensor:
+    """Cosine score of every (enrol, test) index pair; float32 (n_trials).  center=True subtracts the mean x-vector of
+    the set first (computed by the statistics-pooling kernel over the (N, dim) matrix)."""
     _require_cuda(xvecs, enrol, test)
     lib = _lib.load()
     if xvecs.dtype != torch.float32 or enrol.dtype != torch.int32 or test.dtype != torch.int32:
@@ -149,7 +150,10 @@ def cosine_trials(xvecs: torch.Tensor, enrol: torch.Tensor, test: torch.Tensor) 
     if test.numel() != n:
         raise ValueError("enrol and test must have the same length")
     out = torch.empty(n, dtype=torch.float32, device=xvecs.device)
+    mean = None
+    if center:
+        mean = stats_pool_ragged(xvecs, np.zeros(1, np.int64), np.asarray([xvecs.shape[0]], np.int32))[0, : xvecs.shape[1]].contiguous()
     with torch.cuda.device(xvecs.device):
-        check(lib.xvec_cosine_trials(ptr(xvecs), ld, xvecs.shape[1], ptr(enrol.contiguous()), ptr(test.contiguous()), n, ptr(out),
-                                     stream_ptr()))
+        check(lib.xvec_cosine_trials(ptr(xvecs), ld, xvecs.shape[1], ptr(mean), ptr(enrol.contiguous()), ptr(test.contiguous()), n,
+                                     ptr(out), stream_ptr()))
     return out

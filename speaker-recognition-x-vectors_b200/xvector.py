@@ -85,17 +85,17 @@ class XVectorModel(nn.Module):
         if self.training:
             raise RuntimeError("xvec_b200.XVectorModel implements the eval-mode extraction path only; call .eval() first")
 
-    def _plan_for(self, lengths) -> _Plan:
+    def _plan_for(self, lengths, slot: int = 0) -> _Plan:
         lengths = np.asarray(lengths, dtype=np.int64)
         dev = self._device()
-        key = (lengths.tobytes(), str(dev), self.precision)
+        key = (lengths.tobytes(), str(dev), self.precision, slot)
         plan = self._plans.get(key)
         if plan is None:
             layers = list(self.time_context_layers)
             widths = [l.output_size for l in layers[:-1]]
             plan = _Plan(build_layout(lengths, self.lost_frames), dev, self.act_dtype, widths, layers[-1].output_size)
             self._plans[key] = plan
-            while len(self._plans) > 8:
+            while len(self._plans) > 16:
                 self._plans.popitem(last=False)
         else:
             self._plans.move_to_end(key)
@@ -117,15 +117,16 @@ class XVectorModel(nn.Module):
         return ops.tdnn_layer_flat(x2d, w, lin.out_features, [0], b, None, None, relu=relu, out_dtype=out_dtype, cin=lin.in_features)
 
     # ------------------------------------------------------------------ the hot path
-    def pooled_stats_flat(self, flat_x: torch.Tensor, lengths) -> "tuple[torch.Tensor, torch.Tensor | None]":
+    def pooled_stats_flat(self, flat_x: torch.Tensor, lengths, slot: int = 0) -> "tuple[torch.Tensor, torch.Tensor | None]":
         """TDNN stack + statistics pooling over a flat (rows, input_size) float32 frame matrix.
-        Returns (pooled float32 (U, 3000), same in the activation dtype or None)."""
+        Returns (pooled float32 (U, 3000), same in the activation dtype or None).  The returned tensors are scratch of
+        the (lengths, slot) plan: they are overwritten by the next call with the same lengths and slot."""
         self._check_eval()
         if not flat_x.is_cuda:
             raise ValueError("xvec_b200 has no CPU path: move the input (and the model) to a CUDA device")
         if flat_x.dim() != 2 or flat_x.shape[1] != self.input_size:
             raise ValueError(f"expected a flat (rows, {self.input_size}) frame matrix")
-        plan = self._plan_for(lengths)
+        plan = self._plan_for(lengths, slot)
         if plan.layout.rows != flat_x.shape[0]:
             raise ValueError("sum(lengths) does not match the number of rows")
         layers = list(self.time_context_layers)
@@ -150,9 +151,10 @@ class XVectorModel(nn.Module):
             return self._linear(self.segment_layer7, h6, relu=False, out_dtype=torch.float32)
         return self._linear(self.segment_layer6, a, relu=False, out_dtype=torch.float32)  # 6 and "anything else" (main.py:86-87,91-92)
 
-    def extract_x_vec_flat(self, flat_x: torch.Tensor, lengths) -> torch.Tensor:
-        """Ragged extraction: flat (sum(lengths), input_size) frames -> float32 (len(lengths), x_vector_size)."""
-        pooled, pooled_lp = self.pooled_stats_flat(flat_x, lengths)
+    def extract_x_vec_flat(self, flat_x: torch.Tensor, lengths, slot: int = 0) -> torch.Tensor:
+        """Ragged extraction: flat (sum(lengths), input_size) frames -> float32 (len(lengths), x_vector_size).
+        `slot` selects an independent scratch set so that calls on different CUDA streams can overlap."""
+        pooled, pooled_lp = self.pooled_stats_flat(flat_x, lengths, slot)
         return self._head(pooled, pooled_lp, self.x_vec_extract_layer)
 
     # ------------------------------------------------------------------ reference surface

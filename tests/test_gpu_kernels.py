@@ -159,6 +159,9 @@ def test_cast_and_cosine(xb):
     t = torch.randint(0, 50, (1000,), generator=g).int().cuda()
     ref = torch.nn.functional.cosine_similarity(xv[e.long()].double(), xv[t.long()].double(), dim=1)
     assert (xb.ops.cosine_trials(xv, e, t).double() - ref).abs().max().item() < 1e-5
+    xc = xv.double() - xv.double().mean(0)
+    refc = torch.nn.functional.cosine_similarity(xc[e.long()], xc[t.long()], dim=1)
+    assert (xb.ops.cosine_trials(xv, e, t, center=True).double() - refc).abs().max().item() < 1e-5
 
 
 def test_argument_errors(xb):

@@ -125,16 +125,19 @@ def test_config1_batch64_against_oracle(xb, state_dict, precision):
 
 
 def test_trial_decisions_identical(xb, state_dict):
-    """Cosine trial decisions from GPU embeddings == decisions from oracle embeddings at the oracle's EER threshold."""
-    lens = ox.synth_lengths(120, 100, 400, seed=3)
-    utts = ox.synth_ragged(lens, seed=55)
+    """Centred-cosine trial decisions from GPU embeddings == decisions from oracle embeddings at the oracle's EER
+    threshold; the score perturbation must stay inside the oracle's decision margin."""
+    n, nspk = 240, 24
+    lens = ox.synth_lengths(n, 100, 400, seed=3)
+    utts = ox.synth_speaker_utts(lens, nspk, seed=55)
     ref = ox.extract_ragged_t(state_dict, utts, 6).numpy()
-    enrol, test, target = ox.synth_trials(120, 3000, n_speakers=12, seed=4)
-    s_ref = ox.cosine_scores_np(ref, enrol, test)
-    _, thr, margin = ox.eer_threshold_np(s_ref, target)
+    enrol, test, target = ox.synth_trials(n, 6000, n_speakers=nspk, seed=4)
+    s_ref = ox.cosine_scores_np(ref, enrol, test, center=True)
+    eer, thr, margin = ox.eer_threshold_np(s_ref, target)
+    assert eer < 0.05 and margin > 1e-3
     for precision in ("tf32", "bf16"):
         m = _model(xb, state_dict, precision)
         xv = m.extract_x_vec_flat(torch.cat(utts).cuda(), lens)
-        s = xb.ops.cosine_trials(xv, torch.from_numpy(enrol).int().cuda(), torch.from_numpy(test).int().cuda()).cpu().numpy()
+        s = xb.ops.cosine_trials(xv, torch.from_numpy(enrol).int().cuda(), torch.from_numpy(test).int().cuda(), center=True).cpu().numpy()
         assert np.abs(s - s_ref).max() < margin, (precision, np.abs(s - s_ref).max(), margin)
         assert np.array_equal(s >= thr, s_ref >= thr)
