@@ -265,18 +265,21 @@ def instrumented_layer_times(model, x_dev, lengths, n_batches, iters):
     acc = dict.fromkeys(names, 0.0)
     layers = list(model.time_context_layers)
     plan = model._plan_for(lengths, 0)
+    stack, (scale5, shift5) = model._stack_params()
     for it in range(iters + 2):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
         h = _aligned_rows(x_dev[it % n_batches])
         evs[0].record()
         for i, layer in enumerate(layers[:-1]):
-            h = layer.forward_flat(h, out=plan.act[i & 1][:, : layer.output_size])
+            w, bias, offs = stack[i]
+            h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True,
+                                    out=plan.act[i & 1][:, : layer.output_size], cin=layer.input_size)
             evs[i + 1].record()
         last = layers[-1]
-        w, bias, scale, shift = last.prepared(h.dtype)
-        ops.tdnn_pool_fused(h, w, last.output_size, tap_offsets(last.context), bias, plan.row_utt, plan.blk_slot_base, plan.part)
+        w, bias, offs = stack[-1]
+        ops.tdnn_pool_fused(h, w, last.output_size, offs, bias, plan.row_utt, plan.blk_slot_base, plan.part)
         evs[5].record()
-        ops.pool_finalize(plan.part, plan.utt_slot_start, plan.n_pool, last.output_size, scale, shift, out=plan.pooled, out_lp=plan.pooled_lp)
+        ops.pool_finalize(plan.part, plan.utt_slot_start, plan.n_pool, last.output_size, scale5, shift5, out=plan.pooled, out_lp=plan.pooled_lp)
         evs[6].record()
         model._head(plan.pooled, plan.pooled_lp, 6)
         evs[7].record()

@@ -55,6 +55,10 @@ XVEC_API int xvec_device_check(void);
 /* Value left by the device-side pipeline watchdog (0 = never fired). Synchronises the device. */
 XVEC_API int xvec_watchdog_code(void);
 
+/* Developer aid: with XVEC_TRACE=1 in the environment the GEMM kernel records per-tile clock64 stamps of CTA 0;
+ * copies up to n of them to out_host and returns the count (0 when tracing is off). */
+XVEC_API int xvec_debug_trace(long long* out_host, int n);
+
 /* Number of K elements one packed weight row holds: taps * ceil(cin / kc) * kc, kc = 32 (F32) or 64 (BF16). */
 XVEC_API int64_t xvec_packed_k(int cin, int taps, int dtype);
 /* Rows of a packed weight matrix: n rounded up to XVEC_TILE_N. */
@@ -74,8 +78,9 @@ XVEC_API int xvec_pack_weight(const float* w_dev, int n, int taps, int cin, int 
  *   x_dev      (x_rows, cin) of x_dtype, row stride x_ld elements (x_ld*elsize multiple of 16 bytes, base 16-byte aligned)
  *   w_packed   from xvec_pack_weight with the same taps/cin/dtype
  *   tap_offsets_host  taps non-negative row offsets c_j - c_0 (HOST array)
- *   bias_dev   float32 (n) or NULL;  bn_scale_dev/bn_shift_dev float32 (n) or both NULL:
- *              scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale
+ *   bias_dev   float32 or NULL;  bn_scale_dev/bn_shift_dev float32 or both NULL:
+ *              scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale.
+ *              These vectors are read 32 columns at a time: each must be 16-byte aligned and hold ceil(n/32)*32 floats.
  *   y_dev      (rows, n) of y_dtype, row stride y_ld elements.  Input rows beyond x_rows read as zero.
  */
 XVEC_API int xvec_tdnn_layer(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld,
@@ -88,7 +93,7 @@ XVEC_API int xvec_tdnn_layer(const void* x_dev, int x_dtype, int64_t x_rows, int
  * r and r*r into part_dev[slot][2][n] (float32).  BatchNorm of this layer is applied by xvec_pool_finalize.
  * replaces: TdnnLayer #5 (main.py:43) + the reads of torch.mean/torch.std in stat_pool (main.py:59-63).
  *   row_utt_dev        int32 (rows): utterance index of a row that takes part in pooling, -1 for don't-care rows
- *   blk_slot_base_dev  int32 (ceil(rows/128)*4): first partial slot of each 32-row block (slots of a block are
+ *   blk_slot_base_dev  int32 (ceil(rows/256)*8): first partial slot of each 32-row block (slots of a block are
  *                      consecutive, one per utterance with a pooled row in it, in row order)
  */
 XVEC_API int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld,

@@ -23,6 +23,7 @@ _SIGNATURES = {
     "xvec_last_error": (c_char_p, []),
     "xvec_device_check": (c_int, []),
     "xvec_watchdog_code": (c_int, []),
+    "xvec_debug_trace": (c_int, [c_void_p, c_int]),
     "xvec_packed_k": (c_int64, [c_int, c_int, c_int]),
     "xvec_packed_n": (c_int64, [c_int]),
     "xvec_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

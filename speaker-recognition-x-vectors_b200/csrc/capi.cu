@@ -79,6 +79,8 @@ int xvec_watchdog_code(void) {
   return read_watchdog();
 }
 
+int xvec_debug_trace(long long* out_host, int n) { return read_trace(out_host, n); }
+
 int64_t xvec_packed_k(int cin, int taps, int dtype) {
   const int kc = dtype == XVEC_BF16 ? 64 : 32;
   return static_cast<int64_t>(taps) * ((cin + kc - 1) / kc) * kc;

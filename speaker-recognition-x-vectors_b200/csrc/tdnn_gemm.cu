@@ -7,29 +7,38 @@
 // TMA producer simply shifts the row coordinate of the A tile by the tap's frame offset.  Rows past the end of the
 // matrix and channels past Cin are zero-filled by TMA, the packed weights carry matching zero padding.
 //
-// Persistent, warp-specialised CTA (192 threads, 1 CTA/SM):
-//   warp 0      TMA producer        (A tile 128 rows x 128 B, B tile 256 rows x 128 B, 4-stage mbarrier ring)
-//   warp 1      TMEM owner + tcgen05.mma issuer (UMMA 128x256x{16 bf16 | 8 tf32}, fp32 accumulators in TMEM,
-//               two 256-column accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2-5   epilogue: tcgen05.ld -> bias/ReLU/BatchNorm affine -> global store          (EPI_STORE_*)
-//                         or -> per-utterance column sums of r and r^2 (statistics pooling)  (EPI_POOL)
+// One output tile = 256 frames x 256 channels, computed by a CTA PAIR (cluster of 2, tcgen05 cta_group::2): each CTA
+// stages its own 128 frame rows (A) and HALF of the weight tile (B, 128 channels) per 128-byte K chunk, so a CTA moves
+// 32 KiB through shared memory per 128x256x{64 bf16|32 tf32} of its MMA work instead of 48 KiB — v1 of this kernel
+// (single-CTA 128x256 tiles) was bound by shared-memory bandwidth (TMA writes + UMMA operand reads), see DESIGN.md.
+//
+// Persistent, warp-specialised CTA (192 threads, 1 CTA/SM, 74 pairs):
+//   warp 0      TMA producer (both CTAs; completion bytes of both land on the LEADER's full barrier)
+//   warp 1      TMEM owner; in the leader CTA one thread issues tcgen05.mma.cta_group::2 (UMMA 256x256xK, fp32
+//               accumulators in TMEM, two 256-column buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 2-5   epilogue (both CTAs, 128 rows each): tcgen05.ld -> bias/ReLU/BatchNorm affine -> 128B-swizzled smem
+//               staging -> TMA store                                                          (EPI_STORE_*)
+//               or -> per-utterance column sums of r and r^2 (statistics pooling partials)    (EPI_POOL)
 #include "ptx.cuh"
 #include "xvec_internal.h"
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace xvec {
 
-constexpr int BM = 128;
-constexpr int BN = XVEC_TILE_N;  // 256
-constexpr int BK_BYTES = 128;    // one 128B-swizzle atom row: 64 bf16 or 32 tf32 channels
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK_BYTES;  // 16 KiB
-constexpr int B_BYTES = BN * BK_BYTES;  // 32 KiB
+constexpr int BM_CTA = 128;            // frame rows per CTA
+constexpr int BM = 2 * BM_CTA;         // frame rows per tile (CTA pair)
+constexpr int BN = XVEC_TILE_N;        // 256 output channels per tile
+constexpr int BN_CTA = BN / 2;         // weight rows staged by each CTA
+constexpr int BK_BYTES = 128;          // one 128B-swizzle atom row: 64 bf16 or 32 tf32 channels
+constexpr int A_BYTES = BM_CTA * BK_BYTES;  // 16 KiB
+constexpr int B_BYTES = BN_CTA * BK_BYTES;  // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int MAX_NPAD = 1536;          // column parameters staged in shared memory by the store epilogue
-constexpr int TR_LD = 33;               // padded row stride of the per-warp 32x32 transpose tile
+constexpr int TR_LD = 36;              // padded (16-byte aligned) stride of the per-warp transposed 32x32 tile (pool epilogue)
+constexpr int OUT_BUF_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes
 
 enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_POOL = 2 };
 
@@ -45,35 +54,65 @@ struct GemmParams {
   int relu;
   void* out;
   long long ldo;
-  int vec_ok;  // output rows are 16-byte aligned -> vector stores
+  int vec_store;  // output rows are 16-byte aligned -> swizzled smem staging + TMA store; else scalar stores
   const int* row_utt;
   const int* blk_slot_base;
   float* part;
+  unsigned long long pol_a, pol_b, pol_y;  // L2 eviction hints: activations in, weights, activations out
+  long long* trace;  // debug: per-tile clock64 stamps of pair 0 (XVEC_TRACE=1)
+  int dbg;  // debug: bit0 skip tmem loads, bit1 skip output staging+store, bit2 skip epilogue math
 };
 
+// {lo, hi} floats -> packed bf16x2 (lo in the low half), round-to-nearest; the _relu form clamps negatives to 0.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+constexpr int TRACE_TILES = 32;
+constexpr int TRACE_SLOTS = 16;
+__device__ __forceinline__ void trace(const GemmParams& p, int it, int slot) {
+  if (p.trace && blockIdx.x == 0 && it < TRACE_TILES) p.trace[it * TRACE_SLOTS + slot] = clock64();
+}
+
+template <int kEpi>
+constexpr int num_stages() {
+  return 6;
+}
 template <int kEpi>
 constexpr int epi_smem_bytes() {
-  return kEpi == EPI_POOL ? 4 * 32 * TR_LD * 4 : 3 * MAX_NPAD * 4;
+  return kEpi == EPI_POOL ? 4 * 32 * TR_LD * 4 : 4 * 2 * OUT_BUF_BYTES;
 }
 template <int kEpi>
 constexpr int gemm_smem_bytes() {
-  return 1024 + STAGES * STAGE_BYTES + epi_smem_bytes<kEpi>();
+  return 1024 + num_stages<kEpi>() * STAGE_BYTES + epi_smem_bytes<kEpi>();
 }
 
 template <bool kTf32, int kEpi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
+  constexpr int STAGES = num_stages<kEpi>();
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ int tap_off_s[XVEC_MAX_TAPS];
 
-  // SWIZZLE_128B tiles need 1024-byte alignment
+  // SWIZZLE_128B tiles need 1024-byte alignment (same offset in both CTAs of the pair)
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* epi_smem = base + STAGES * STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
   constexpr int BKE = kTf32 ? 32 : 64;  // elements per 128-byte chunk
   const int kblocks = p.taps * p.cpt;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -82,216 +121,301 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (kEpi != EPI_POOL) tma_prefetch_desc(&tmY);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx (bytes of both CTAs)
+      mbar_init(&empty_bar[s], 1);  // leader's multicast commit
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);  // one arrive per epilogue warp
+      mbar_init(&tfull_bar[b], 1);   // leader's multicast commit
+      mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp of both CTAs (on the leader's barrier)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
-  if constexpr (kEpi != EPI_POOL) {
-    float* cb = reinterpret_cast<float*>(epi_smem);
-    const int npad = p.n_tiles * BN;
-    for (int i = threadIdx.x; i < npad; i += GEMM_THREADS) {
-      const bool ok = i < p.n;
-      cb[i] = (ok && p.bias) ? p.bias[i] : 0.f;
-      cb[MAX_NPAD + i] = (ok && p.scale) ? p.scale[i] : 1.f;
-      cb[2 * MAX_NPAD + i] = (ok && p.shift) ? p.shift[i] : 0.f;
-    }
-  }
+  if (warp == 1) tmem_alloc_pair<TMEM_COLS>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t / p.n_tiles) * BM;
-        const int n0 = (t % p.n_tiles) * BN;
+      int pit = 0;
+      for (int t = pair; t < total_tiles; t += n_pairs, ++pit) {
+        const int m0 = (t / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA;
+        const int n0 = (t % p.n_tiles) * BN + static_cast<int>(rank) * BN_CTA;
         for (int kb = 0; kb < kblocks; ++kb) {
           const int tap = kb / p.cpt;
           const int ch = kb - tap * p.cpt;
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (kb == 0) trace(p, pit, 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = base + stage * STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &full_bar[stage], ch * BKE, m0 + tap_off_s[tap]);
-          tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BKE, n0);
+          tma_load_2d_pair(sa, &tmA, leader_full, ch * BKE, m0 + tap_off_s[tap], p.pol_a);
+          tma_load_2d_pair(sa + A_BYTES, &tmB, leader_full, kb * BKE, n0, p.pol_b);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = pair; t < total_tiles; t += n_pairs, ++it) {
         const int buf = it & 1;
         const uint32_t use = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[buf], use ^ 1u, 2);  // epilogue has drained this accumulator buffer
+        trace(p, it, 1);
+        mbar_wait(&tempty_bar[buf], use ^ 1u, 2);  // both CTAs' epilogues have drained this accumulator buffer
         tc_fence_after();
+        trace(p, it, 2);
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
+          if (kb == 0) trace(p, it, 3);
           const uint32_t a_addr = smem_u32(base + stage * STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K inside the swizzle atom
-            umma_ss<kTf32>(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
+            umma_ss_pair<kTf32>(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage], 0x3);  // smem slot free in both CTAs once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[buf]);  // accumulator complete
+        umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
+        trace(p, it, 4);
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, 128 rows each)
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int m0 = (t / p.n_tiles) * BM;
+    int store_seq = 0;
+    for (int t = pair; t < total_tiles; t += n_pairs, ++it) {
+      const int m0 = (t / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA;
       const int n0 = (t % p.n_tiles) * BN;
       const int buf = it & 1;
       const uint32_t use = (it >> 1) & 1;
+      if (warp == 2 && lane == 0) trace(p, it, 5);
       mbar_wait(&tfull_bar[buf], use, 4);
       tc_fence_after();
+      if (warp == 2 && lane == 0) trace(p, it, 6);
       const uint32_t tbase = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
-      const int row = m0 + q * 32 + lane;
+      const int row0 = m0 + q * 32;
+      const int row = row0 + lane;
 
       if constexpr (kEpi == EPI_POOL) {
+        // per warp: 32 rows x 32 columns at a time, transposed through smem so that lane == column; column sums of
+        // r = relu(acc + bias) and r^2 per utterance present in the 32-row block, packed f32x2 arithmetic.
         float* tr = reinterpret_cast<float*>(epi_smem) + (warp - 2) * (32 * TR_LD);
         const int my_u = (row < p.rows) ? __ldg(p.row_utt + row) : -1;
-        const int slot0 = __ldg(p.blk_slot_base + (m0 >> 5) + q);
+        const int slot0 = __ldg(p.blk_slot_base + (row0 >> 5));
         const unsigned valid = __ballot_sync(0xffffffffu, my_u >= 0);
         for (int c = 0; c < BN && n0 + c < p.n; c += 32) {
+          if (valid == 0u) break;  // block has no pooled rows (warp-uniform)
           uint32_t v[32];
           tmem_ld_32x32(tbase + c, v);
           tmem_ld_wait();
-          if (valid == 0u) continue;  // block has no pooled rows (uniform)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tr[lane * TR_LD + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) tr[j * TR_LD + lane] = __uint_as_float(v[j]);  // tr[column][row]
           __syncwarp();
           const int col = n0 + c + lane;  // this lane now owns one column
           const float b = (col < p.n && p.bias) ? __ldg(p.bias + col) : 0.f;
+          float4 z[8];                    // the column's 32 rows
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[i] = *reinterpret_cast<const float4*>(tr + lane * TR_LD + 4 * i);
+          __syncwarp();
+          const float2 b2 = make_float2(b, b);
           unsigned remaining = valid;
           int seg = 0;
           while (remaining) {  // one pass per utterance present in this 32-row block (warp-uniform)
             const int lo = __ffs(remaining) - 1;
             const int u = __shfl_sync(0xffffffffu, my_u, lo);
             const unsigned m = __ballot_sync(0xffffffffu, my_u == u);
-            const int hi = 32 - __clz(m);
-            float s = 0.f, ss = 0.f;
-            if (lo == 0 && hi == 32) {
+            float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+            if (m == 0xffffffffu) {
 #pragma unroll
-              for (int r = 0; r < 32; ++r) {
-                const float z = fmaxf(tr[r * TR_LD + lane] + b, 0.f);
-                s += z;
-                ss = fmaf(z, z, ss);
+              for (int i = 0; i < 8; ++i) {
+                float2 a = __fadd2_rn(make_float2(z[i].x, z[i].y), b2);
+                float2 d = __fadd2_rn(make_float2(z[i].z, z[i].w), b2);
+                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f);
+                d.x = fmaxf(d.x, 0.f); d.y = fmaxf(d.y, 0.f);
+                s2 = __fadd2_rn(s2, a);
+                q2 = __ffma2_rn(a, a, q2);
+                s2 = __fadd2_rn(s2, d);
+                q2 = __ffma2_rn(d, d, q2);
               }
             } else {
-              for (int r = lo; r < hi; ++r) {
-                const float z = fmaxf(tr[r * TR_LD + lane] + b, 0.f);
-                s += z;
-                ss = fmaf(z, z, ss);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float2 a = __fadd2_rn(make_float2(z[i].x, z[i].y), b2);
+                float2 d = __fadd2_rn(make_float2(z[i].z, z[i].w), b2);
+                a.x = ((m >> (4 * i + 0)) & 1u) ? fmaxf(a.x, 0.f) : 0.f;
+                a.y = ((m >> (4 * i + 1)) & 1u) ? fmaxf(a.y, 0.f) : 0.f;
+                d.x = ((m >> (4 * i + 2)) & 1u) ? fmaxf(d.x, 0.f) : 0.f;
+                d.y = ((m >> (4 * i + 3)) & 1u) ? fmaxf(d.y, 0.f) : 0.f;
+                s2 = __fadd2_rn(s2, a);
+                q2 = __ffma2_rn(a, a, q2);
+                s2 = __fadd2_rn(s2, d);
+                q2 = __ffma2_rn(d, d, q2);
               }
             }
             if (col < p.n) {
               float* dst = p.part + static_cast<size_t>(slot0 + seg) * 2 * p.n + col;
-              dst[0] = s;
-              dst[p.n] = ss;
+              dst[0] = s2.x + s2.y;
+              dst[p.n] = q2.x + q2.y;
             }
             remaining &= ~m;
             ++seg;
           }
-          __syncwarp();
         }
       } else {
-        const float* cb = reinterpret_cast<const float*>(epi_smem);
-        for (int c = 0; c < BN && n0 + c < p.n; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tbase + c, v);
-          tmem_ld_wait();
-          const int col0 = n0 + c;
-          float o[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(cb + col0 + j4);
-            const float4 sc = *reinterpret_cast<const float4*>(cb + MAX_NPAD + col0 + j4);
-            const float4 sh = *reinterpret_cast<const float4*>(cb + 2 * MAX_NPAD + col0 + j4);
-            float a0 = __uint_as_float(v[j4 + 0]) + bb.x, a1 = __uint_as_float(v[j4 + 1]) + bb.y;
-            float a2 = __uint_as_float(v[j4 + 2]) + bb.z, a3 = __uint_as_float(v[j4 + 3]) + bb.w;
-            if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-            o[j4 + 0] = fmaf(a0, sc.x, sh.x);
-            o[j4 + 1] = fmaf(a1, sc.y, sh.y);
-            o[j4 + 2] = fmaf(a2, sc.z, sh.z);
-            o[j4 + 3] = fmaf(a3, sc.w, sh.w);
+        uint8_t* out_stage = epi_smem + (warp - 2) * (2 * OUT_BUF_BYTES);  // two 32-row x 128-byte staging boxes
+        constexpr int OUT_ES = kEpi == EPI_STORE_BF16 ? 2 : 4;
+        constexpr int GROUP_COLS = 128 / OUT_ES;     // columns per TMA-store box (128 bytes per row)
+        constexpr int CHUNKS = GROUP_COLS / 32;      // tcgen05.ld chunks per box
+        for (int c = 0; c < BN && n0 + c < p.n; c += GROUP_COLS) {
+          uint8_t* ob = out_stage + (store_seq & 1) * OUT_BUF_BYTES;
+          if (p.vec_store && !(p.dbg & 2)) {
+            if (lane == 0) tma_store_wait_read<1>();  // the store that last used this box has read it
+            __syncwarp();
           }
-          if (row < p.rows) {
-            const bool full = (col0 + 32 <= p.n) && p.vec_ok;
-            if constexpr (kEpi == EPI_STORE_BF16) {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-              if (full) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
+          for (int cc = 0; cc < CHUNKS; ++cc) {
+            const int col0 = n0 + c + cc * 32;
+            if (col0 >= p.n) break;  // warp-uniform; the box is clipped by TMA
+            uint32_t v[32];
+            if (!(p.dbg & 1)) {
+              if (warp == 2 && lane == 0 && c == 0 && cc == 0) trace(p, it, 8);
+              tmem_ld_32x32(tbase + c + cc * 32, v);
+              tmem_ld_wait();
+              if (warp == 2 && lane == 0 && c == 0 && cc == 0) trace(p, it, 9);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = lane + j;
+            }
+            // bias (+ReLU, + optional BatchNorm affine); column parameters are warp-uniform read-only loads
+            float o[32];
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+            if (p.scale == nullptr) {
+#pragma unroll
+              for (int j4 = 0; j4 < 32; j4 += 4) {
+                const float4 bb = p.bias ? __ldg(bp + (j4 >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 0]), __uint_as_float(v[j4 + 1])), make_float2(bb.x, bb.y));
+                const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), make_float2(bb.z, bb.w));
+                o[j4 + 0] = a.x; o[j4 + 1] = a.y; o[j4 + 2] = d.x; o[j4 + 3] = d.y;
+              }
+              if (p.relu && kEpi != EPI_STORE_BF16) {  // bf16 output: ReLU is folded into the convert below
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+              }
+            } else {
+              const float4* sp = reinterpret_cast<const float4*>(p.scale + col0);
+              const float4* hp = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+              for (int j4 = 0; j4 < 32; j4 += 4) {
+                const float4 bb = p.bias ? __ldg(bp + (j4 >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 sc = __ldg(sp + (j4 >> 2));
+                const float4 sh = __ldg(hp + (j4 >> 2));
+                float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 0]), __uint_as_float(v[j4 + 1])), make_float2(bb.x, bb.y));
+                float2 d = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), make_float2(bb.z, bb.w));
+                if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); d.x = fmaxf(d.x, 0.f); d.y = fmaxf(d.y, 0.f); }
+                a = __ffma2_rn(a, make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                d = __ffma2_rn(d, make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                o[j4 + 0] = a.x; o[j4 + 1] = a.y; o[j4 + 2] = d.x; o[j4 + 3] = d.y;
+              }
+            }
+            const bool cvt_relu = p.relu && p.scale == nullptr;  // ReLU not applied yet (bf16 fast path)
+            if (warp == 2 && lane == 0 && c == 0 && cc == 0) trace(p, it, 10);
+            if (p.dbg & 2) {
+              if (o[0] == 123.456f && o[31] == 1.f) ob[lane] = 1;
+            } else if (p.vec_store) {
+              // row `lane` of the box, 16-byte pieces XOR-swizzled like CU_TENSOR_MAP_SWIZZLE_128B expects
+              uint8_t* orow = ob + lane * 128;
+              if constexpr (kEpi == EPI_STORE_BF16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
                   uint4 w;
-                  __nv_bfloat162 h0 = __floats2bfloat162_rn(o[j + 0], o[j + 1]);
-                  __nv_bfloat162 h1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-                  __nv_bfloat162 h2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]);
-                  __nv_bfloat162 h3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-                  w.x = *reinterpret_cast<uint32_t*>(&h0);
-                  w.y = *reinterpret_cast<uint32_t*>(&h1);
-                  w.z = *reinterpret_cast<uint32_t*>(&h2);
-                  w.w = *reinterpret_cast<uint32_t*>(&h3);
-                  *reinterpret_cast<uint4*>(dst + j) = w;
+                  if (cvt_relu) {
+                    w.x = pack_bf16x2_relu(o[8 * j + 0], o[8 * j + 1]);
+                    w.y = pack_bf16x2_relu(o[8 * j + 2], o[8 * j + 3]);
+                    w.z = pack_bf16x2_relu(o[8 * j + 4], o[8 * j + 5]);
+                    w.w = pack_bf16x2_relu(o[8 * j + 6], o[8 * j + 7]);
+                  } else {
+                    w.x = pack_bf16x2(o[8 * j + 0], o[8 * j + 1]);
+                    w.y = pack_bf16x2(o[8 * j + 2], o[8 * j + 3]);
+                    w.z = pack_bf16x2(o[8 * j + 4], o[8 * j + 5]);
+                    w.w = pack_bf16x2(o[8 * j + 6], o[8 * j + 7]);
+                  }
+                  const int piece = cc * 4 + j;
+                  *reinterpret_cast<uint4*>(orow + ((piece ^ (lane & 7)) << 4)) = w;
                 }
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.n) dst[j] = __float2bfloat16_rn(o[j]);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                  *reinterpret_cast<float4*>(orow + ((j ^ (lane & 7)) << 4)) = w;
+                }
               }
-            } else {
-              float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-              if (full) {
+            } else if (row < p.rows) {
+              if constexpr (kEpi == EPI_STORE_BF16) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.n) dst[j] = __float2bfloat16_rn(cvt_relu ? fmaxf(o[j], 0.f) : o[j]);
               } else {
+                float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (col0 + j < p.n) dst[j] = o[j];
               }
             }
           }
+          if (p.vec_store && !(p.dbg & 2)) {
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+              if (row0 < p.rows) tma_store_2d(&tmY, ob, n0 + c, row0, p.pol_y);  // rows / columns past the matrix are clipped
+              tma_store_commit();
+            }
+            if (warp == 2 && lane == 0 && c == 0) trace(p, it, 11);
+            ++store_seq;
+          }
         }
       }
-      // all of this warp's TMEM reads of the buffer are complete -> hand it back to the MMA issuer
+      // all of this warp's TMEM reads of the buffer are complete -> hand it back to the leader's MMA issuer
+      if (warp == 2 && lane == 0) trace(p, it, 12);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (warp == 2 && lane == 0) trace(p, it, 13);
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+      if (warp == 2 && lane == 0) trace(p, it, 7);
+    }
+    if constexpr (kEpi != EPI_POOL) {
+      if (lane == 0) tma_store_wait_all();
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer may still be reading our smem / signalling our barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    tmem_dealloc_pair<TMEM_COLS>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+static long long* g_trace_buf = nullptr;
+
 static int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                         uint32_t box_inner, uint32_t box_outer) {
   PFN_encodeTiled enc = get_encode_tiled();
@@ -311,7 +435,7 @@ static int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t i
 }
 
 template <bool kTf32, int kEpi>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const GemmParams& p, int grid, cudaStream_t st) {
   static bool configured[64] = {};  // per instantiation and device
   constexpr int smem = gemm_smem_bytes<kEpi>();
   int dev = 0;
@@ -321,8 +445,19 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  tdnn_gemm_kernel<kTf32, kEpi><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tdnn_gemm_kernel<kTf32, kEpi>, ta, tb, ty, p);
   if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "tdnn_gemm_kernel launch: %s", cudaGetErrorString(e));
   return XVEC_OK;
 }
@@ -354,7 +489,8 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
     if (tap_offsets[j] < 0) return set_error(XVEC_E_ARG, "tap offsets must be non-negative");
     p.tap_off[j] = tap_offsets[j];
   }
-  if (!pool && p.n_tiles * BN > MAX_NPAD) return set_error(XVEC_E_ARG, "n > %d is not supported by the store epilogue", MAX_NPAD);
+  if (!pool && ((reinterpret_cast<uintptr_t>(bias) & 15u) || (reinterpret_cast<uintptr_t>(scale) & 15u) || (reinterpret_cast<uintptr_t>(shift) & 15u)))
+    return set_error(XVEC_E_ARG, "bias / bn_scale / bn_shift must be 16-byte aligned (and hold ceil(n/32)*32 floats)");
   p.bias = bias;
   p.scale = scale;
   p.shift = shift;
@@ -362,26 +498,68 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
   p.out = y;
   p.ldo = y_ld;
   const int64_t yes = y_dtype == XVEC_BF16 ? 2 : 4;
-  p.vec_ok = (!pool && (reinterpret_cast<uintptr_t>(y) & 15u) == 0 && (y_ld * yes) % 16 == 0) ? 1 : 0;
+  p.vec_store = (!pool && (reinterpret_cast<uintptr_t>(y) & 15u) == 0 && (y_ld * yes) % 16 == 0) ? 1 : 0;
   if (!pool && y_ld < n) return set_error(XVEC_E_ARG, "y_ld < n");
   p.row_utt = row_utt;
   p.blk_slot_base = blk_slot_base;
   p.part = part;
+  {
+    static int dbg = -1;
+    static long long* trace_buf = nullptr;
+    if (dbg < 0) {
+      const char* e = getenv("XVEC_DBG");
+      dbg = e ? atoi(e) : 0;
+      if (getenv("XVEC_TRACE")) cudaMalloc(&trace_buf, TRACE_TILES * TRACE_SLOTS * sizeof(long long));
+    }
+    p.dbg = dbg;
+    static const unsigned long long pol_tab[3] = {L2_EVICT_NORMAL, L2_EVICT_FIRST, L2_EVICT_LAST};
+    static int hint[3] = {-1, 0, 0};
+    if (hint[0] < 0) {
+      const char* h = getenv("XVEC_L2HINT");  // three digits: activations-in, weights, activations-out (0 normal, 1 first, 2 last)
+      const char* def = "122";
+      if (!h || strlen(h) != 3) h = def;
+      for (int i = 0; i < 3; ++i) hint[i] = (h[i] >= '0' && h[i] <= '2') ? h[i] - '0' : 0;
+    }
+    p.pol_a = pol_tab[hint[0]];
+    p.pol_b = pol_tab[hint[1]];
+    p.pol_y = pol_tab[hint[2]];
+    p.trace = trace_buf;
+    g_trace_buf = trace_buf;
+  }
 
-  CUtensorMap ta, tb;
-  rc = make_tmap_2d(&ta, x, x_dtype, static_cast<uint64_t>(cin), static_cast<uint64_t>(x_rows), static_cast<uint64_t>(x_ld), bke, BM);
+  CUtensorMap ta, tb, ty;
+  rc = make_tmap_2d(&ta, x, x_dtype, static_cast<uint64_t>(cin), static_cast<uint64_t>(x_rows), static_cast<uint64_t>(x_ld), bke, BM_CTA);
   if (rc) return rc;
   const uint64_t kpad = static_cast<uint64_t>(taps) * p.cpt * bke;
-  rc = make_tmap_2d(&tb, w_packed, x_dtype, kpad, static_cast<uint64_t>(p.n_tiles) * BN, kpad, bke, BN);
+  rc = make_tmap_2d(&tb, w_packed, x_dtype, kpad, static_cast<uint64_t>(p.n_tiles) * BN, kpad, bke, BN_CTA);
   if (rc) return rc;
+  if (p.vec_store) {
+    rc = make_tmap_2d(&ty, y, y_dtype, static_cast<uint64_t>(n), static_cast<uint64_t>(rows), static_cast<uint64_t>(y_ld),
+                      static_cast<uint32_t>(128 / yes), 32);
+    if (rc) return rc;
+  } else {
+    ty = ta;  // unused by the kernel
+  }
 
   const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
-  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  const int max_pairs = num_sms() / 2;
+  const int pairs = static_cast<int>(tiles < max_pairs ? tiles : max_pairs);
+  const int grid = 2 * pairs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (pool) return tf32 ? launch<true, EPI_POOL>(ta, tb, p, grid, st) : launch<false, EPI_POOL>(ta, tb, p, grid, st);
+  if (pool) return tf32 ? launch<true, EPI_POOL>(ta, tb, ty, p, grid, st) : launch<false, EPI_POOL>(ta, tb, ty, p, grid, st);
   if (y_dtype == XVEC_BF16)
-    return tf32 ? launch<true, EPI_STORE_BF16>(ta, tb, p, grid, st) : launch<false, EPI_STORE_BF16>(ta, tb, p, grid, st);
-  return tf32 ? launch<true, EPI_STORE_F32>(ta, tb, p, grid, st) : launch<false, EPI_STORE_F32>(ta, tb, p, grid, st);
+    return tf32 ? launch<true, EPI_STORE_BF16>(ta, tb, ty, p, grid, st) : launch<false, EPI_STORE_BF16>(ta, tb, ty, p, grid, st);
+  return tf32 ? launch<true, EPI_STORE_F32>(ta, tb, ty, p, grid, st) : launch<false, EPI_STORE_F32>(ta, tb, ty, p, grid, st);
+}
+
+static long long* g_trace_buf_decl_guard = nullptr;
+int read_trace(long long* out_host, int n) {
+  (void)g_trace_buf_decl_guard;
+  if (!g_trace_buf) return 0;
+  const int m = n < TRACE_TILES * TRACE_SLOTS ? n : TRACE_TILES * TRACE_SLOTS;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out_host, g_trace_buf, m * sizeof(long long), cudaMemcpyDeviceToHost);
+  return m;
 }
 
 int read_watchdog() {

@@ -25,5 +25,6 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
                   void* y, int y_dtype, int64_t y_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part,
                   int64_t rows, bool pool, void* stream);
 int read_watchdog();
+int read_trace(long long* out_host, int n);
 
 }  // namespace xvec

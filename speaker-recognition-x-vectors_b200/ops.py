@@ -23,6 +23,20 @@ def _rowmajor_2d(t: torch.Tensor, what: str):
     return t.stride(0)
 
 
+def pad32(vec: torch.Tensor | None) -> torch.Tensor | None:
+    """Column-parameter vectors are read 32 floats at a time by the epilogue: float32, contiguous, padded with zeros."""
+    if vec is None:
+        return None
+    v = vec.detach().to(torch.float32).contiguous()
+    n = v.numel()
+    m = (n + 31) // 32 * 32
+    if m == n:
+        return v
+    out = torch.zeros(m, dtype=torch.float32, device=v.device)
+    out[:n] = v
+    return out
+
+
 def pack_weight(weight: torch.Tensor, taps: int, cin: int, dtype: torch.dtype) -> torch.Tensor:
     """nn.Linear weight (n, taps*cin) float32 -> packed (n_pad, k_pad) operand for xvec_tdnn_layer."""
     _require_cuda(weight)
@@ -53,6 +67,9 @@ def tdnn_layer_flat(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
         raise ValueError("out must be (rows, n)")
     if w_packed.dtype != x.dtype:
         raise ValueError("packed weights and activations must share a dtype")
+    need = (n + 31) // 32 * 32
+    bias, bn_scale, bn_shift = [v if v is None or (v.numel() >= need and v.dtype == torch.float32) else pad32(v)
+                                for v in (bias, bn_scale, bn_shift)]
     offs = taps_array(offsets)
     with torch.cuda.device(x.device):
         check(lib.xvec_tdnn_layer(ptr(x), dtype_code(x.dtype), rows, cin, x_ld, ptr(w_packed), n, offs, len(offsets),
@@ -70,7 +87,7 @@ def tdnn_pool_fused(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
     rows = x.shape[0]
     if row_utt.dtype != torch.int32 or blk_slot_base.dtype != torch.int32 or part.dtype != torch.float32:
         raise ValueError("row_utt / blk_slot_base must be int32, part float32")
-    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 127) // 128) * 4 or not part.is_contiguous():
+    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * 8 or not part.is_contiguous():
         raise ValueError("pooling bookkeeping arrays are too small for this frame matrix")
     offs = taps_array(offsets)
     with torch.cuda.device(x.device):

@@ -57,18 +57,28 @@ class TdnnLayer(nn.Module):
             return hit[1]
         offs = tap_offsets(self.context)
         w = ops.pack_weight(self.linear.weight, len(offs), self.input_size, dtype)
-        bias = None if self.linear.bias is None else self.linear.bias.detach().float().contiguous()
+        bias = ops.pad32(self.linear.bias)
         scale = shift = None
         if self.batch_norm:
             n = self.norm
             gamma = n.weight.detach().double() if n.weight is not None else torch.ones_like(n.running_var, dtype=torch.float64)
             beta = n.bias.detach().double() if n.bias is not None else torch.zeros_like(n.running_var, dtype=torch.float64)
             s = gamma / torch.sqrt(n.running_var.detach().double() + n.eps)
-            scale = s.float().contiguous()
-            shift = (beta - n.running_mean.detach().double() * s).float().contiguous()
+            scale = ops.pad32(s.float())
+            shift = ops.pad32((beta - n.running_mean.detach().double() * s).float())
         out = (w, bias, scale, shift)
         self._prep[dtype] = (fp, out)
         return out
+
+    def bn_affine64(self):
+        """(scale, shift) of this layer's eval-mode BatchNorm in float64, or None."""
+        if not self.batch_norm:
+            return None
+        n = self.norm
+        gamma = n.weight.detach().double() if n.weight is not None else torch.ones_like(n.running_var, dtype=torch.float64)
+        beta = n.bias.detach().double() if n.bias is not None else torch.zeros_like(n.running_var, dtype=torch.float64)
+        s = gamma / torch.sqrt(n.running_var.detach().double() + n.eps)
+        return s, beta - n.running_mean.detach().double() * s
 
     def _check_eval(self):
         if self.training and (self.batch_norm or self.dropout_p):

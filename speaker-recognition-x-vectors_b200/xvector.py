@@ -101,6 +101,37 @@ class XVectorModel(nn.Module):
             self._plans.move_to_end(key)
         return plan
 
+    def _stack_params(self):
+        """Packed operands of the five TDNN layers for the fused pipeline, with every layer's eval-mode BatchNorm folded
+        FORWARD into the next layer (BN comes after ReLU, tdnn_layer.py:30-39, so it cannot fold into its own layer):
+            W'_i = W_i . diag(s_{i-1} (x) 1_k),   b'_i = b_i + W_i . (h_{i-1} (x) 1_k)
+        so each epilogue is just relu(acc + b'); the last layer's BN is folded through the statistics by
+        xvec_pool_finalize (mean' = s.mean + h, std' = |s|.std).  Computed once in float64, cached until parameters change.
+        Layer 1 reads the float32 MFCCs (TF32 math) in both precisions."""
+        layers = list(self.time_context_layers)
+        fp = tuple(l._fingerprint() for l in layers) + (self.precision,)
+        hit = self._fc_prep.get("stack")
+        if hit is not None and hit[0] == fp:
+            return hit[1]
+        out, prev = [], None
+        for i, layer in enumerate(layers):
+            layer._check_eval()
+            offs = tap_offsets(layer.context)
+            W = layer.linear.weight.detach().double()
+            b = (layer.linear.bias.detach().double() if layer.linear.bias is not None
+                 else torch.zeros(layer.output_size, dtype=torch.float64, device=W.device))
+            if prev is not None:
+                s, h = prev
+                b = b + W @ h.repeat(len(offs))
+                W = W * s.repeat(len(offs))[None, :]
+            dtype = torch.float32 if i == 0 else self.act_dtype
+            out.append((ops.pack_weight(W.float(), len(offs), layer.input_size, dtype), ops.pad32(b.float()), offs))
+            prev = layer.bn_affine64()
+        last_bn = (None, None) if prev is None else (prev[0].float().contiguous(), prev[1].float().contiguous())
+        res = (out, last_bn)
+        self._fc_prep["stack"] = (fp, res)
+        return res
+
     def _fc(self, lin: nn.Linear, dtype):
         fp = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr() if lin.bias is not None else 0,
               lin.bias._version if lin.bias is not None else 0, str(lin.weight.device))
@@ -108,7 +139,7 @@ class XVectorModel(nn.Module):
         if hit is not None and hit[0] == fp:
             return hit[1]
         w = ops.pack_weight(lin.weight, 1, lin.in_features, dtype)
-        b = None if lin.bias is None else lin.bias.detach().float().contiguous()
+        b = ops.pad32(lin.bias)
         self._fc_prep[(id(lin), dtype)] = (fp, (w, b))
         return w, b
 
@@ -132,15 +163,16 @@ class XVectorModel(nn.Module):
         layers = list(self.time_context_layers)
         if flat_x.dtype != torch.float32:
             flat_x = flat_x.float()
+        stack, (scale5, shift5) = self._stack_params()
         h = _aligned_rows(flat_x)  # layer 1 always reads float32 frames (TF32 math): no cast pass over the input
         for i, layer in enumerate(layers[:-1]):
+            w, bias, offs = stack[i]
             out = plan.act[i & 1][:, : layer.output_size]
-            h = layer.forward_flat(h, out=out)
+            h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True, out=out, cin=layer.input_size)
         last = layers[-1]
-        last._check_eval()
-        w, bias, scale, shift = last.prepared(h.dtype)
-        ops.tdnn_pool_fused(h, w, last.output_size, tap_offsets(last.context), bias, plan.row_utt, plan.blk_slot_base, plan.part)
-        ops.pool_finalize(plan.part, plan.utt_slot_start, plan.n_pool, last.output_size, scale, shift, out=plan.pooled,
+        w, bias, offs = stack[-1]
+        ops.tdnn_pool_fused(h, w, last.output_size, offs, bias, plan.row_utt, plan.blk_slot_base, plan.part)
+        ops.pool_finalize(plan.part, plan.utt_slot_start, plan.n_pool, last.output_size, scale5, shift5, out=plan.pooled,
                           out_lp=plan.pooled_lp)
         return plan.pooled, plan.pooled_lp
 

@@ -78,7 +78,7 @@ def test_layout_bookkeeping_is_exact(lens):
     assert (lay.n_pool == np.asarray(lens) - 14).all()
     for u, (s, l) in enumerate(zip(lay.starts, lens)):
         assert (lay.row_utt[s:s + l - 14] == u).all() and (lay.row_utt[s + l - 14:s + l] == -1).all()
-    assert lay.blk_slot_base.shape[0] == -(-lay.rows // 128) * 4
+    assert lay.blk_slot_base.shape[0] == -(-lay.rows // 256) * 8
     rng = np.random.default_rng(0)
     r = np.abs(rng.standard_normal((lay.rows, 8)))
     got = _emulate_fused_pool(lay, r)
