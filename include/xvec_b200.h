@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XVEC_ABI_VERSION 1
+#define XVEC_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define XVEC_API __attribute__((visibility("default")))
@@ -82,11 +82,18 @@ XVEC_API int xvec_pack_weight(const float* w_dev, int n, int taps, int cin, int 
  *              scale = gamma/sqrt(running_var+eps), shift = beta - running_mean*scale.
  *              These vectors are read 32 columns at a time: each must be 16-byte aligned and hold ceil(n/32)*32 floats.
  *   y_dev      (rows, n) of y_dtype, row stride y_ld elements.  Input rows beyond x_rows read as zero.
+ *   splitk_ws_dev / splitk_ws_bytes  optional scratch (16-byte aligned) of at least xvec_splitk_workspace_bytes(...)
+ *              bytes: when the GEMM has too few output tiles to fill the GPU (segment6: a few hundred rows, K = 3000)
+ *              the K loop is split over CTA pairs into this workspace and a fixed-order second pass applies the
+ *              epilogue.  NULL / too small = no split (slower, same result up to fp32 summation order).
  */
 XVEC_API int xvec_tdnn_layer(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld,
                     const void* w_packed_dev, int n, const int32_t* tap_offsets_host, int taps,
                     const float* bias_dev, const float* bn_scale_dev, const float* bn_shift_dev, int relu,
-                    void* y_dev, int y_dtype, int64_t y_ld, int64_t rows, void* stream);
+                    void* y_dev, int y_dtype, int64_t y_ld, int64_t rows, void* splitk_ws_dev, int64_t splitk_ws_bytes,
+                    void* stream);
+/* Scratch bytes xvec_tdnn_layer can use for split-K on this shape (0 = it would not split). */
+XVEC_API int64_t xvec_splitk_workspace_bytes(int64_t rows, int cin, int taps, int n, int dtype);
 
 /* Last TDNN layer fused with the first half of statistics pooling: the (rows x n) activation
  * r = relu(W.x + bias) is never written; per XVEC_POOL_BLOCK-row block and utterance the kernel emits column sums of

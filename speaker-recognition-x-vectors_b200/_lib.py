@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libxvec_b200.so")
 F32, BF16 = 0, 1
 E_ARG, E_CUDA, E_DEVICE = -1, -2, -3
 TILE_N, POOL_BLOCK, POOL_CHUNK, MAX_TAPS = 256, 32, 128, 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _SIGNATURES = {
     "xvec_abi_version": (c_int, []),
@@ -28,7 +28,8 @@ _SIGNATURES = {
     "xvec_packed_n": (c_int64, [c_int]),
     "xvec_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "xvec_tdnn_layer": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int, POINTER(c_int32), c_int,
-                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "xvec_splitk_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
     "xvec_tdnn_pool_fused": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int, POINTER(c_int32), c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "xvec_stats_pool_partial": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -85,14 +85,20 @@ int64_t xvec_packed_k(int cin, int taps, int dtype) {
   const int kc = dtype == XVEC_BF16 ? 64 : 32;
   return static_cast<int64_t>(taps) * ((cin + kc - 1) / kc) * kc;
 }
+int64_t xvec_splitk_workspace_bytes(int64_t rows, int cin, int taps, int n, int dtype) {
+  if (rows <= 0 || cin <= 0 || taps < 1 || n <= 0) return 0;
+  return splitk_workspace_bytes(rows, cin, taps, n, dtype);
+}
 int64_t xvec_packed_n(int n) { return static_cast<int64_t>((n + XVEC_TILE_N - 1) / XVEC_TILE_N) * XVEC_TILE_N; }
 
 int xvec_tdnn_layer(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld, const void* w_packed_dev, int n,
                     const int32_t* tap_offsets_host, int taps, const float* bias_dev, const float* bn_scale_dev,
-                    const float* bn_shift_dev, int relu, void* y_dev, int y_dtype, int64_t y_ld, int64_t rows, void* stream) {
+                    const float* bn_shift_dev, int relu, void* y_dev, int y_dtype, int64_t y_ld, int64_t rows, void* splitk_ws_dev,
+                    int64_t splitk_ws_bytes, void* stream) {
   if (!tap_offsets_host) return set_error(XVEC_E_ARG, "tap_offsets_host is NULL");
   return gemm_dispatch(x_dev, x_dtype, x_rows, cin, x_ld, w_packed_dev, n, tap_offsets_host, taps, bias_dev, bn_scale_dev,
-                       bn_shift_dev, relu, y_dev, y_dtype, y_ld, nullptr, nullptr, nullptr, rows, false, stream);
+                       bn_shift_dev, relu, y_dev, y_dtype, y_ld, nullptr, nullptr, nullptr, rows, false, splitk_ws_dev, splitk_ws_bytes,
+                       stream);
 }
 
 int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld, const void* w_packed_dev, int n,
@@ -100,7 +106,7 @@ int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin
                          const int32_t* blk_slot_base_dev, float* part_dev, int64_t rows, void* stream) {
   if (!tap_offsets_host) return set_error(XVEC_E_ARG, "tap_offsets_host is NULL");
   return gemm_dispatch(x_dev, x_dtype, x_rows, cin, x_ld, w_packed_dev, n, tap_offsets_host, taps, bias_dev, nullptr, nullptr, 1,
-                       nullptr, XVEC_F32, 0, row_utt_dev, blk_slot_base_dev, part_dev, rows, true, stream);
+                       nullptr, XVEC_F32, 0, row_utt_dev, blk_slot_base_dev, part_dev, rows, true, nullptr, 0, stream);
 }
 
 }  // extern "C"

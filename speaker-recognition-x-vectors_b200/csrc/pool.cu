@@ -82,7 +82,22 @@ pool_finalize_kernel(const float* __restrict__ part, const int* __restrict__ slo
   if (col >= p) return;
   const int sl0 = slot_start[u], sl1 = slot_start[u + 1];
   double S = 0.0, Q = 0.0;
-  for (int sl = sl0; sl < sl1; ++sl) {
+  int sl = sl0;
+  for (; sl + 4 <= sl1; sl += 4) {  // 8 independent loads in flight, summed in slot order
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* src = part + static_cast<size_t>(sl + i) * 2 * p + col;
+      a[i] = src[0];
+      b[i] = src[p];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      S += static_cast<double>(a[i]);
+      Q += static_cast<double>(b[i]);
+    }
+  }
+  for (; sl < sl1; ++sl) {
     const float* src = part + static_cast<size_t>(sl) * 2 * p + col;
     S += static_cast<double>(src[0]);
     Q += static_cast<double>(src[p]);

@@ -12,11 +12,11 @@
 // 32 KiB through shared memory per 128x256x{64 bf16|32 tf32} of its MMA work instead of 48 KiB — v1 of this kernel
 // (single-CTA 128x256 tiles) was bound by shared-memory bandwidth (TMA writes + UMMA operand reads), see DESIGN.md.
 //
-// Persistent, warp-specialised CTA (192 threads, 1 CTA/SM, 74 pairs):
+// Persistent, warp-specialised CTA (320 threads, 1 CTA/SM, 74 pairs):
 //   warp 0      TMA producer (both CTAs; completion bytes of both land on the LEADER's full barrier)
 //   warp 1      TMEM owner; in the leader CTA one thread issues tcgen05.mma.cta_group::2 (UMMA 256x256xK, fp32
 //               accumulators in TMEM, two 256-column buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2-5   epilogue (both CTAs, 128 rows each): tcgen05.ld -> bias/ReLU/BatchNorm affine -> 128B-swizzled smem
+//   warps 2-9   epilogue (both CTAs, 128 rows each; 2 warps per TMEM lane quarter, each half of the columns): tcgen05.ld -> bias/ReLU/BatchNorm affine -> 128B-swizzled smem
 //               staging -> TMA store                                                          (EPI_STORE_*)
 //               or -> per-utterance column sums of r and r^2 (statistics pooling partials)    (EPI_POOL)
 #include "ptx.cuh"
@@ -35,10 +35,12 @@ constexpr int BK_BYTES = 128;          // one 128B-swizzle atom row: 64 bf16 or 
 constexpr int A_BYTES = BM_CTA * BK_BYTES;  // 16 KiB
 constexpr int B_BYTES = BN_CTA * BK_BYTES;  // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;             // two per TMEM lane quarter, each owning half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int TR_LD = 36;              // padded (16-byte aligned) stride of the per-warp transposed 32x32 tile (pool epilogue)
 constexpr int OUT_BUF_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes
+constexpr int OUT_BUFS = 2;              // staging boxes per epilogue warp (TMA stores in flight)
 
 enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_POOL = 2 };
 
@@ -58,6 +60,7 @@ struct GemmParams {
   const int* row_utt;
   const int* blk_slot_base;
   float* part;
+  int ksplit, kb_per_split, rows_pad;  // split-K: tile t also selects a K range; partial sums go to row s*rows_pad + r
   unsigned long long pol_a, pol_b, pol_y;  // L2 eviction hints: activations in, weights, activations out
   long long* trace;  // debug: per-tile clock64 stamps of pair 0 (XVEC_TRACE=1)
   int dbg;  // debug: bit0 skip tmem loads, bit1 skip output staging+store, bit2 skip epilogue math
@@ -83,11 +86,11 @@ __device__ __forceinline__ void trace(const GemmParams& p, int it, int slot) {
 
 template <int kEpi>
 constexpr int num_stages() {
-  return 6;
+  return 5;
 }
 template <int kEpi>
 constexpr int epi_smem_bytes() {
-  return kEpi == EPI_POOL ? 4 * 32 * TR_LD * 4 : 4 * 2 * OUT_BUF_BYTES;
+  return kEpi == EPI_POOL ? EPI_WARPS * 32 * TR_LD * 4 : EPI_WARPS * OUT_BUFS * OUT_BUF_BYTES;
 }
 template <int kEpi>
 constexpr int gemm_smem_bytes() {
@@ -115,7 +118,8 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_pairs = gridDim.x >> 1;
   constexpr int BKE = kTf32 ? 32 : 64;  // elements per 128-byte chunk
   const int kblocks = p.taps * p.cpt;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int mn_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = mn_tiles * p.ksplit;
 
   if (threadIdx.x < XVEC_MAX_TAPS) tap_off_s[threadIdx.x] = p.tap_off[threadIdx.x];
   if (warp == 0 && lane == 0) {
@@ -128,7 +132,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);   // leader's multicast commit
-      mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp of both CTAs (on the leader's barrier)
+      mbar_init(&tempty_bar[b], 2 * EPI_WARPS);  // one arrive per epilogue warp of both CTAs (on the leader's barrier)
     }
     fence_mbar_init();
   }
@@ -146,13 +150,15 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int pit = 0;
       for (int t = pair; t < total_tiles; t += n_pairs, ++pit) {
-        const int m0 = (t / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA;
-        const int n0 = (t % p.n_tiles) * BN + static_cast<int>(rank) * BN_CTA;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
+        const int m0 = (tt / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA;
+        const int n0 = (tt % p.n_tiles) * BN + static_cast<int>(rank) * BN_CTA;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int tap = kb / p.cpt;
           const int ch = kb - tap * p.cpt;
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-          if (kb == 0) trace(p, pit, 0);
+          if (kb == kb0) trace(p, pit, 0);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = base + stage * STAGE_BYTES;
@@ -177,16 +183,17 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         trace(p, it, 2);
         const uint32_t d = tmem_base + buf * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int kb0 = (t / mn_tiles) * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
-          if (kb == 0) trace(p, it, 3);
+          if (kb == kb0) trace(p, it, 3);
           const uint32_t a_addr = smem_u32(base + stage * STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K inside the swizzle atom
-            umma_ss_pair<kTf32>(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss_pair<kTf32>(d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           umma_commit_pair(&empty_bar[stage], 0x3);  // smem slot free in both CTAs once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -196,12 +203,15 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (both CTAs, 128 rows each)
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;             // TMEM lane quarter this warp may read
+    const int cbeg = ((warp - 2) >> 2) * (BN / 2);  // this warp's half of the tile's columns
+    const int cend = cbeg + BN / 2;
     int it = 0;
     int store_seq = 0;
     for (int t = pair; t < total_tiles; t += n_pairs, ++it) {
-      const int m0 = (t / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA;
-      const int n0 = (t % p.n_tiles) * BN;
+      const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
+      const int m0 = (tt / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA;
+      const int n0 = (tt % p.n_tiles) * BN;
       const int buf = it & 1;
       const uint32_t use = (it >> 1) & 1;
       if (warp == 2 && lane == 0) trace(p, it, 5);
@@ -219,7 +229,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int my_u = (row < p.rows) ? __ldg(p.row_utt + row) : -1;
         const int slot0 = __ldg(p.blk_slot_base + (row0 >> 5));
         const unsigned valid = __ballot_sync(0xffffffffu, my_u >= 0);
-        for (int c = 0; c < BN && n0 + c < p.n; c += 32) {
+        for (int c = cbeg; c < cend && n0 + c < p.n; c += 32) {
           if (valid == 0u) break;  // block has no pooled rows (warp-uniform)
           uint32_t v[32];
           tmem_ld_32x32(tbase + c, v);
@@ -278,14 +288,14 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else {
-        uint8_t* out_stage = epi_smem + (warp - 2) * (2 * OUT_BUF_BYTES);  // two 32-row x 128-byte staging boxes
+        uint8_t* out_stage = epi_smem + (warp - 2) * (OUT_BUFS * OUT_BUF_BYTES);  // 32-row x 128-byte staging boxes
         constexpr int OUT_ES = kEpi == EPI_STORE_BF16 ? 2 : 4;
         constexpr int GROUP_COLS = 128 / OUT_ES;     // columns per TMA-store box (128 bytes per row)
         constexpr int CHUNKS = GROUP_COLS / 32;      // tcgen05.ld chunks per box
-        for (int c = 0; c < BN && n0 + c < p.n; c += GROUP_COLS) {
-          uint8_t* ob = out_stage + (store_seq & 1) * OUT_BUF_BYTES;
+        for (int c = cbeg; c < cend && n0 + c < p.n; c += GROUP_COLS) {
+          uint8_t* ob = out_stage + (store_seq % OUT_BUFS) * OUT_BUF_BYTES;
           if (p.vec_store && !(p.dbg & 2)) {
-            if (lane == 0) tma_store_wait_read<1>();  // the store that last used this box has read it
+            if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();  // the store that last used this box has read it
             __syncwarp();
           }
 #pragma unroll
@@ -294,10 +304,10 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (col0 >= p.n) break;  // warp-uniform; the box is clipped by TMA
             uint32_t v[32];
             if (!(p.dbg & 1)) {
-              if (warp == 2 && lane == 0 && c == 0 && cc == 0) trace(p, it, 8);
+              if (warp == 2 && lane == 0 && c == cbeg && cc == 0) trace(p, it, 8);
               tmem_ld_32x32(tbase + c + cc * 32, v);
               tmem_ld_wait();
-              if (warp == 2 && lane == 0 && c == 0 && cc == 0) trace(p, it, 9);
+              if (warp == 2 && lane == 0 && c == cbeg && cc == 0) trace(p, it, 9);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = lane + j;
@@ -334,7 +344,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             const bool cvt_relu = p.relu && p.scale == nullptr;  // ReLU not applied yet (bf16 fast path)
-            if (warp == 2 && lane == 0 && c == 0 && cc == 0) trace(p, it, 10);
+            if (warp == 2 && lane == 0 && c == cbeg && cc == 0) trace(p, it, 10);
             if (p.dbg & 2) {
               if (o[0] == 123.456f && o[31] == 1.f) ob[lane] = 1;
             } else if (p.vec_store) {
@@ -380,13 +390,15 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (p.vec_store && !(p.dbg & 2)) {
+            if (warp == 2 && lane == 0 && c == cbeg) trace(p, it, 14);
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();
+            if (warp == 2 && lane == 0 && c == cbeg) trace(p, it, 15);
             if (lane == 0) {
-              if (row0 < p.rows) tma_store_2d(&tmY, ob, n0 + c, row0, p.pol_y);  // rows / columns past the matrix are clipped
+              if (row0 < p.rows) tma_store_2d(&tmY, ob, n0 + c, ks * p.rows_pad + row0, p.pol_y);  // rows / columns past the matrix are clipped
               tma_store_commit();
             }
-            if (warp == 2 && lane == 0 && c == 0) trace(p, it, 11);
+            if (warp == 2 && lane == 0 && c == cbeg) trace(p, it, 11);
             ++store_seq;
           }
         }
@@ -410,6 +422,28 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+  }
+}
+
+// Split-K second pass: y[r, c] = epi( sum_s ws[s*rows_pad + r, c] ) in fixed split order (deterministic).
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, int rows, int rows_pad, int n, int ws_ld, const float* __restrict__ bias,
+                     const float* __restrict__ scale, const float* __restrict__ shift, int relu, void* __restrict__ out, int out_bf16,
+                     long long ldo) {
+  const long long total = static_cast<long long>(rows) * n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / n);
+    const int c = static_cast<int>(i - static_cast<long long>(r) * n);
+    float a = 0.f;
+    for (int s = 0; s < ksplit; ++s) a += ws[(static_cast<size_t>(s) * rows_pad + r) * ws_ld + c];
+    if (bias) a += bias[c];
+    if (relu) a = fmaxf(a, 0.f);
+    if (scale) a = fmaf(a, scale[c], shift[c]);
+    if (out_bf16)
+      reinterpret_cast<__nv_bfloat16*>(out)[static_cast<size_t>(r) * ldo + c] = __float2bfloat16_rn(a);
+    else
+      reinterpret_cast<float*>(out)[static_cast<size_t>(r) * ldo + c] = a;
   }
 }
 
@@ -462,10 +496,33 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   return XVEC_OK;
 }
 
+// Split-K plan for GEMMs with too few output tiles to fill the machine (segment6/7: a few hundred rows, K = 3000).
+static void splitk_plan(int64_t rows, int n, int kblocks, int* ksplit, int* kb_per_split) {
+  const int64_t mn = ((rows + BM - 1) / BM) * ((n + BN - 1) / BN);
+  const int pairs = num_sms() / 2;
+  *ksplit = 1;
+  *kb_per_split = kblocks;
+  if (mn * 4 > pairs || kblocks < 8) return;
+  int want = static_cast<int>(pairs / mn);
+  if (want > kblocks / 2) want = kblocks / 2;
+  if (want < 2) return;
+  *kb_per_split = (kblocks + want - 1) / want;
+  *ksplit = (kblocks + *kb_per_split - 1) / *kb_per_split;
+}
+
+int64_t splitk_workspace_bytes(int64_t rows, int cin, int taps, int n, int dtype) {
+  const int bke = dtype == XVEC_F32 ? 32 : 64;
+  int ksplit, kbs;
+  splitk_plan(rows, n, taps * ((cin + bke - 1) / bke), &ksplit, &kbs);
+  if (ksplit <= 1) return 0;
+  const int64_t rows_pad = (rows + BM - 1) / BM * BM;
+  return static_cast<int64_t>(ksplit) * rows_pad * ((n + BN - 1) / BN * BN) * 4;
+}
+
 int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x_ld, const void* w_packed, int n,
                   const int32_t* tap_offsets, int taps, const float* bias, const float* scale, const float* shift, int relu,
                   void* y, int y_dtype, int64_t y_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part,
-                  int64_t rows, bool pool, void* stream) {
+                  int64_t rows, bool pool, void* ws, int64_t ws_bytes, void* stream) {
   int rc = device_check();
   if (rc) return rc;
   if (!x || !w_packed || (!pool && !y) || (pool && (!row_utt || !blk_slot_base || !part)))
@@ -503,6 +560,29 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
   p.row_utt = row_utt;
   p.blk_slot_base = blk_slot_base;
   p.part = part;
+  p.ksplit = 1;
+  p.kb_per_split = taps * p.cpt;
+  p.rows_pad = p.m_tiles * BM;
+  // split-K: partial sums go to the caller's workspace, a second pass applies the epilogue
+  const int64_t ws_need = pool ? 0 : splitk_workspace_bytes(rows, cin, taps, n, x_dtype);
+  const bool split = ws_need > 0 && ws != nullptr && ws_bytes >= ws_need && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0;
+  const int ws_ld = p.n_tiles * BN;
+  void* final_y = y;
+  const int final_dtype = y_dtype;
+  const int64_t final_ld = y_ld;
+  if (split) {
+    splitk_plan(rows, n, taps * p.cpt, &p.ksplit, &p.kb_per_split);
+    p.bias = nullptr;
+    p.scale = nullptr;
+    p.shift = nullptr;
+    p.relu = 0;
+    p.out = ws;
+    p.ldo = ws_ld;
+    p.vec_store = 1;
+    y = ws;
+    y_dtype = XVEC_F32;
+    y_ld = ws_ld;
+  }
   {
     static int dbg = -1;
     static long long* trace_buf = nullptr;
@@ -534,14 +614,15 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
   rc = make_tmap_2d(&tb, w_packed, x_dtype, kpad, static_cast<uint64_t>(p.n_tiles) * BN, kpad, bke, BN_CTA);
   if (rc) return rc;
   if (p.vec_store) {
-    rc = make_tmap_2d(&ty, y, y_dtype, static_cast<uint64_t>(n), static_cast<uint64_t>(rows), static_cast<uint64_t>(y_ld),
-                      static_cast<uint32_t>(128 / yes), 32);
+    const uint64_t yrows = split ? static_cast<uint64_t>(p.ksplit) * p.rows_pad : static_cast<uint64_t>(rows);
+    rc = make_tmap_2d(&ty, y, y_dtype, static_cast<uint64_t>(n), yrows, static_cast<uint64_t>(y_ld),
+                      static_cast<uint32_t>(128 / (y_dtype == XVEC_BF16 ? 2 : 4)), 32);
     if (rc) return rc;
   } else {
     ty = ta;  // unused by the kernel
   }
 
-  const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+  const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles * p.ksplit;
   const int max_pairs = num_sms() / 2;
   const int pairs = static_cast<int>(tiles < max_pairs ? tiles : max_pairs);
   const int grid = 2 * pairs;
@@ -549,12 +630,20 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
   if (pool) return tf32 ? launch<true, EPI_POOL>(ta, tb, ty, p, grid, st) : launch<false, EPI_POOL>(ta, tb, ty, p, grid, st);
   if (y_dtype == XVEC_BF16)
     return tf32 ? launch<true, EPI_STORE_BF16>(ta, tb, ty, p, grid, st) : launch<false, EPI_STORE_BF16>(ta, tb, ty, p, grid, st);
-  return tf32 ? launch<true, EPI_STORE_F32>(ta, tb, ty, p, grid, st) : launch<false, EPI_STORE_F32>(ta, tb, ty, p, grid, st);
+  rc = tf32 ? launch<true, EPI_STORE_F32>(ta, tb, ty, p, grid, st) : launch<false, EPI_STORE_F32>(ta, tb, ty, p, grid, st);
+  if (rc || !split) return rc;
+  const long long total = rows * static_cast<long long>(n);
+  long long blocks = (total + 255) / 256;
+  if (blocks > num_sms() * 8LL) blocks = num_sms() * 8LL;
+  splitk_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const float*>(ws), p.ksplit, static_cast<int>(rows), p.rows_pad, n,
+                                                                    ws_ld, bias, scale, shift, relu, final_y, final_dtype == XVEC_BF16 ? 1 : 0,
+                                                                    final_ld);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "splitk_reduce_kernel launch: %s", cudaGetErrorString(e));
+  return XVEC_OK;
 }
 
-static long long* g_trace_buf_decl_guard = nullptr;
 int read_trace(long long* out_host, int n) {
-  (void)g_trace_buf_decl_guard;
   if (!g_trace_buf) return 0;
   const int m = n < TRACE_TILES * TRACE_SLOTS ? n : TRACE_TILES * TRACE_SLOTS;
   cudaDeviceSynchronize();

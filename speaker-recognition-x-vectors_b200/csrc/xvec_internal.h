@@ -23,7 +23,8 @@ PFN_encodeTiled get_encode_tiled();
 int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x_ld, const void* w_packed, int n,
                   const int32_t* tap_offsets, int taps, const float* bias, const float* scale, const float* shift, int relu,
                   void* y, int y_dtype, int64_t y_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part,
-                  int64_t rows, bool pool, void* stream);
+                  int64_t rows, bool pool, void* ws, int64_t ws_bytes, void* stream);
+int64_t splitk_workspace_bytes(int64_t rows, int cin, int taps, int n, int dtype);
 int read_watchdog();
 int read_trace(long long* out_host, int n);
 

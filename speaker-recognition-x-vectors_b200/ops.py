@@ -53,7 +53,8 @@ def pack_weight(weight: torch.Tensor, taps: int, cin: int, dtype: torch.dtype) -
 
 
 def tdnn_layer_flat(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bias=None, bn_scale=None, bn_shift=None,
-                    relu: bool = True, out: torch.Tensor | None = None, out_dtype: torch.dtype | None = None, cin: int | None = None):
+                    relu: bool = True, out: torch.Tensor | None = None, out_dtype: torch.dtype | None = None, cin: int | None = None,
+                    workspace: torch.Tensor | None = None):
     """y[r] = bn(relu(sum_j W_j x[r + offsets[j]] + bias)) over a flat (rows, cin) frame matrix; returns (rows, n)."""
     _require_cuda(x, w_packed, bias, bn_scale, bn_shift, out)
     lib = _lib.load()
@@ -71,11 +72,18 @@ def tdnn_layer_flat(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
     bias, bn_scale, bn_shift = [v if v is None or (v.numel() >= need and v.dtype == torch.float32) else pad32(v)
                                 for v in (bias, bn_scale, bn_shift)]
     offs = taps_array(offsets)
+    ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
     with torch.cuda.device(x.device):
         check(lib.xvec_tdnn_layer(ptr(x), dtype_code(x.dtype), rows, cin, x_ld, ptr(w_packed), n, offs, len(offsets),
                                   ptr(bias), ptr(bn_scale), ptr(bn_shift), int(bool(relu)), ptr(out), dtype_code(out.dtype),
-                                  y_ld, rows, stream_ptr()))
+                                  y_ld, rows, ptr(workspace), ws_bytes, stream_ptr()))
     return out
+
+
+def splitk_workspace(rows: int, cin: int, taps: int, n: int, dtype: torch.dtype, device) -> torch.Tensor | None:
+    """Scratch for split-K on this GEMM shape, or None when the shape fills the GPU without it."""
+    nbytes = _lib.load().xvec_splitk_workspace_bytes(rows, cin, taps, n, dtype_code(dtype))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes > 0 else None
 
 
 def tdnn_pool_fused(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bias, row_utt: torch.Tensor,

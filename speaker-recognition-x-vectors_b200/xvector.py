@@ -145,7 +145,11 @@ class XVectorModel(nn.Module):
 
     def _linear(self, lin: nn.Linear, x2d: torch.Tensor, relu: bool, out_dtype) -> torch.Tensor:
         w, b = self._fc(lin, x2d.dtype)
-        return ops.tdnn_layer_flat(x2d, w, lin.out_features, [0], b, None, None, relu=relu, out_dtype=out_dtype, cin=lin.in_features)
+        key = ("ws", x2d.shape[0], lin.in_features, lin.out_features, x2d.dtype, str(x2d.device), torch.cuda.current_stream().cuda_stream)
+        if key not in self._fc_prep:
+            self._fc_prep[key] = ops.splitk_workspace(x2d.shape[0], lin.in_features, 1, lin.out_features, x2d.dtype, x2d.device)
+        return ops.tdnn_layer_flat(x2d, w, lin.out_features, [0], b, None, None, relu=relu, out_dtype=out_dtype, cin=lin.in_features,
+                                   workspace=self._fc_prep[key])
 
     # ------------------------------------------------------------------ the hot path
     def pooled_stats_flat(self, flat_x: torch.Tensor, lengths, slot: int = 0) -> "tuple[torch.Tensor, torch.Tensor | None]":

@@ -76,6 +76,27 @@ def test_tdnn_layer_matches_reference(xb, dtype, rows, cin, n, offs):
     assert xb._lib.load().xvec_watchdog_code() == 0
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,cin,n", [(256, 3000, 512), (100, 512, 512), (700, 3000, 96)])
+def test_split_k_matches_reference(xb, dtype, rows, cin, n):
+    """Few output tiles + long K (segment6/7): K is split over CTA pairs into a workspace, second pass applies the epilogue."""
+    g = torch.Generator().manual_seed(rows + cin)
+    x = torch.randn(rows, cin, generator=g).cuda().to(dtype)
+    W = torch.randn(n, cin, generator=g) / cin ** 0.5
+    b = torch.randn(n, generator=g) * 0.1
+    wp = xb.ops.pack_weight(W.cuda(), 1, cin, dtype)
+    ws = xb.ops.splitk_workspace(rows, cin, 1, n, dtype, "cuda")
+    assert ws is not None
+    Wr = W.to(dtype).float() if dtype == torch.bfloat16 else W
+    for relu, out_dtype in ((False, torch.float32), (True, dtype)):
+        y = xb.ops.tdnn_layer_flat(x, wp, n, [0], b.cuda(), None, None, relu=relu, out_dtype=out_dtype, workspace=ws)
+        y0 = xb.ops.tdnn_layer_flat(x, wp, n, [0], b.cuda(), None, None, relu=relu, out_dtype=out_dtype)
+        _check(y, _ref_layer(x.float().cpu(), Wr, b, [0], relu=relu), dtype)
+        assert (y.float() - y0.float()).abs().max().item() < 2e-2 * y0.float().abs().max().item()
+        assert torch.equal(y, xb.ops.tdnn_layer_flat(x, wp, n, [0], b.cuda(), None, None, relu=relu, out_dtype=out_dtype, workspace=ws))
+    assert xb.ops.splitk_workspace(76800, 512, 3, 512, dtype, "cuda") is None   # big GEMMs never split
+
+
 def test_tdnn_layer_many_tiles_exercises_pipeline_wraparound(xb):
     # > 148*2 tiles per CTA round and > 4 stages: phases of every barrier wrap several times
     rows, cin, n, offs = 148 * 128 * 3 + 77, 512, 512, [0, 2, 4]
