@@ -24,7 +24,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH, FRAMES, CEPS, N_UTTS = 256, 300, 24, 1024          # BASELINE.json configs[1]
+BATCH, FRAMES, CEPS, N_UTTS = int(os.environ.get("XVEC_BENCH_BATCH", "256")), 300, 24, 1024  # BASELINE.json configs[1]
+N_UTTS = (N_UTTS // BATCH) * BATCH
 FLOPS_L = [122_880, 1_572_864, 1_572_864, 524_288, 1_536_000]  # per output frame, SURVEY §8d
 LOST = [4, 8, 14, 14, 14]
 SEG6_FLOPS = 3_072_000

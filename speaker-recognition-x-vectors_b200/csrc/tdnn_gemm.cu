@@ -79,7 +79,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
 }
 
 constexpr int TRACE_TILES = 32;
-constexpr int TRACE_SLOTS = 16;
+constexpr int TRACE_SLOTS = 32;
 __device__ __forceinline__ void trace(const GemmParams& p, int it, int slot) {
   if (p.trace && blockIdx.x == 0 && it < TRACE_TILES) p.trace[it * TRACE_SLOTS + slot] = clock64();
 }
@@ -159,6 +159,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int ch = kb - tap * p.cpt;
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           if (kb == kb0) trace(p, pit, 0);
+          if (kb - kb0 < 8) trace(p, pit, 16 + kb - kb0);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
           const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = base + stage * STAGE_BYTES;
@@ -188,6 +189,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
           if (kb == kb0) trace(p, it, 3);
+          if (kb - kb0 < 8) trace(p, it, 24 + kb - kb0);
           const uint32_t a_addr = smem_u32(base + stage * STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);

@@ -13,10 +13,11 @@ for cin in [int(v) for v in os.environ.get('KS','128,512').split(',')]:
     for _ in range(3):
         ops.tdnn_layer_flat(x, w, n, [0], b, None, None, relu=True, out=out)
     torch.cuda.synchronize()
-    buf = np.zeros(32 * 16, dtype=np.int64)
+    buf = np.zeros(32 * 32, dtype=np.int64)
     m = lib.xvec_debug_trace(buf.ctypes.data_as(ctypes.c_void_p), buf.size)
-    tr = buf.reshape(32, 16)[:16]
+    tr = buf.reshape(32, 32)[:16]
     t0 = tr[0, 0]
     print(f"K={cin}: per tile stamps (cycles since first load issue): prod_first_load, mma_enter, mma_tempty_ok, mma_full0_ok, mma_commit_issued, epi_enter, epi_tfull_ok, epi_done")
     for it in range(4, 14):
         print(it, " ".join(f"{int(v - t0):7d}" for v in tr[it][:8]), "| epi rel tfull_ok:", " ".join(f"{int(v - tr[it][6]):6d}" for v in list(tr[it][8:11]) + list(tr[it][14:16]) + list(tr[it][11:14])), f"done {int(tr[it][7]-tr[it][6])}")
+        print("      load issue->ready per chunk:", " ".join(f"{int(tr[it][24+k]-tr[it][16+k]):6d}" for k in range(8)), "| mma ready gaps:", " ".join(f"{int(tr[it][24+k]-tr[it][24+k-1]):5d}" for k in range(1,8)))
