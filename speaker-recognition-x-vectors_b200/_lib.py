@@ -11,7 +11,7 @@ import threading
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libxvec_b200.so")
+LIB_PATH = os.environ.get("XVEC_LIB") or os.path.join(HERE, "libxvec_b200.so")  # XVEC_LIB: developer A/B builds
 
 F32, BF16 = 0, 1
 E_ARG, E_CUDA, E_DEVICE = -1, -2, -3

@@ -18,6 +18,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// One lane of a fully converged warp (warp-uniform control flow keeps addresses/descriptors in uniform registers; only the
+// single-thread instructions — TMA, tcgen05.mma, tcgen05.commit — are predicated on the elected lane).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -90,6 +98,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// L2 prefetch of a tile (no shared-memory destination): turns a later TMA load of the same box into an L2 hit.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
 // CTA-pair variant: the data lands in this CTA's shared memory, the completion bytes are signalled on a barrier
 // given by its shared::cluster address (the leader CTA's barrier).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0, int32_t c1,
@@ -182,6 +194,90 @@ __device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, u
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+// One K step of the CTA-pair mainloop as a single instruction group, issued by a converged warp:
+//   - every lane first probes (try_wait, non-blocking) the barriers the NEXT step will need, so that the ~100+ cycle
+//     latency of the probe overlaps the MMA issue instead of sitting on the critical path of the issuing warp,
+//   - the elected lane issues the four tcgen05.mma of this 128-byte K chunk (32 bytes of K each) and the commits that
+//     release the operand stages.
+// Returns bit0 = next A barrier already complete, bit1 = next B barrier already complete.
+// One producer step of the CTA-pair mainloop as a single instruction group (converged warp): probe the empty barrier of
+// the NEXT stage first (non-blocking; its latency overlaps the TMA issue), then the elected lane arms the leader's full
+// barrier (leader only) and issues the two tensor loads of this stage.  Returns 1 if the next stage was seen free.
+__device__ __forceinline__ uint32_t tma_step_pair(uint32_t elected, uint32_t is_leader, uint32_t full_bar_local, uint32_t full_bar_leader,
+                                                  uint32_t tx_bytes, uint32_t smem_a, const CUtensorMap* map_a, int32_t a0, int32_t a1,
+                                                  uint64_t pol_a, uint32_t smem_b, const CUtensorMap* map_b, int32_t b0, int32_t b1,
+                                                  uint64_t pol_b, uint32_t probe_bar, uint32_t probe_par) {
+  uint32_t rdy;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pl, pw;\n\t"
+      "setp.ne.b32 pe, %1, 0;\n\t"
+      "setp.ne.b32 pl, %2, 0;\n\t"
+      "and.pred pl, pl, pe;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [%15], %16;\n\t"
+      "@pl mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %5;\n\t"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%6], [%7, {%8, %9}], [%4], %10;\n\t"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%11], [%12, {%13, %14}], [%4], %17;\n\t"
+      "selp.u32 %0, 1, 0, pw;\n\t"
+      "}"
+      : "=r"(rdy)
+      : "r"(elected), "r"(is_leader), "r"(full_bar_local), "r"(full_bar_leader), "r"(tx_bytes), "r"(smem_a),
+        "l"(reinterpret_cast<uint64_t>(map_a)), "r"(a0), "r"(a1), "l"(pol_a), "r"(smem_b), "l"(reinterpret_cast<uint64_t>(map_b)),
+        "r"(b0), "r"(b1), "r"(probe_bar), "r"(probe_par), "l"(pol_b)
+      : "memory");
+  return rdy;
+}
+
+enum { STEP_COMMIT_A = 1, STEP_COMMIT_B = 2, STEP_PROBE_A = 4, STEP_PROBE_B = 8 };
+template <bool kTf32>
+__device__ __forceinline__ uint32_t umma_step_pair(uint32_t elected, uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                                   uint32_t acc0, uint32_t flags, uint32_t commit_a_bar, uint32_t commit_b_bar,
+                                                   uint32_t probe_a_bar, uint32_t probe_a_par, uint32_t probe_b_bar,
+                                                   uint32_t probe_b_par) {
+  uint32_t rdy;
+#define XVEC_STEP_BODY(KIND)                                                                                      \
+  asm volatile(                                                                                                   \
+      "{\n\t"                                                                                                     \
+      ".reg .pred pe, pacc, pt, pca, pcb, ppa, ppb, pwa, pwb;\n\t"                                                \
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"                                                                     \
+      ".reg .b32 ra, rb, f;\n\t"                                                                                  \
+      ".reg .b16 mk;\n\t"                                                                                         \
+      "mov.b16 mk, 3;\n\t"                                                                                        \
+      "setp.ne.b32 pe, %1, 0;\n\t"                                                                                \
+      "setp.ne.b32 pacc, %6, 0;\n\t"                                                                              \
+      "setp.eq.b32 pt, 0, 0;\n\t"                                                                                 \
+      "and.b32 f, %7, 4;\n\tsetp.ne.b32 ppa, f, 0;\n\t"                                                          \
+      "and.b32 f, %7, 8;\n\tsetp.ne.b32 ppb, f, 0;\n\t"                                                          \
+      "setp.ne.b32 pwa, 0, 0;\n\t"                                                                                \
+      "setp.ne.b32 pwb, 0, 0;\n\t"                                                                                \
+      "@ppa mbarrier.try_wait.parity.shared::cta.b64 pwa, [%10], %11;\n\t"                                        \
+      "@ppb mbarrier.try_wait.parity.shared::cta.b64 pwb, [%12], %13;\n\t"                                        \
+      "add.u64 a1, %3, 2;\n\tadd.u64 a2, %3, 4;\n\tadd.u64 a3, %3, 6;\n\t"                                      \
+      "add.u64 b1, %4, 2;\n\tadd.u64 b2, %4, 4;\n\tadd.u64 b3, %4, 6;\n\t"                                      \
+      "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%2], %3, %4, %5, pacc;\n\t"                                   \
+      "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%2], a1, b1, %5, pt;\n\t"                                     \
+      "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%2], a2, b2, %5, pt;\n\t"                                     \
+      "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%2], a3, b3, %5, pt;\n\t"                                     \
+      "and.b32 f, %7, 2;\n\tsetp.ne.b32 pcb, f, 0;\n\tand.pred pcb, pcb, pe;\n\t"                               \
+      "and.b32 f, %7, 1;\n\tsetp.ne.b32 pca, f, 0;\n\tand.pred pca, pca, pe;\n\t"                               \
+      "@pcb tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], mk;\n\t" \
+      "@pca tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], mk;\n\t" \
+      "selp.u32 ra, 1, 0, pwa;\n\t"                                                                               \
+      "selp.u32 rb, 2, 0, pwb;\n\t"                                                                               \
+      "or.b32 %0, ra, rb;\n\t"                                                                                    \
+      "}"                                                                                                         \
+      : "=r"(rdy)                                                                                                 \
+      : "r"(elected), "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc0), "r"(flags), "r"(commit_a_bar),        \
+        "r"(commit_b_bar), "r"(probe_a_bar), "r"(probe_a_par), "r"(probe_b_bar), "r"(probe_b_par)                 \
+      : "memory")
+  if constexpr (kTf32) {
+    XVEC_STEP_BODY("tf32");
+  } else {
+    XVEC_STEP_BODY("f16");
+  }
+#undef XVEC_STEP_BODY
+  return rdy;
 }
 // Pair commit: arrives on the same-offset barrier of every CTA in `cta_mask` once the issued MMAs complete.
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {

@@ -35,12 +35,12 @@ constexpr int BK_BYTES = 128;          // one 128B-swizzle atom row: 64 bf16 or 
 constexpr int A_BYTES = BM_CTA * BK_BYTES;  // 16 KiB
 constexpr int B_BYTES = BN_CTA * BK_BYTES;  // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_WARPS = 8;             // two per TMEM lane quarter, each owning half of the tile's columns
+constexpr int EPI_WARPS = 8;             // two per TMEM lane quarter, each owning half (128) of the tile's columns
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
-constexpr int TR_LD = 36;              // padded (16-byte aligned) stride of the per-warp transposed 32x32 tile (pool epilogue)
 constexpr int OUT_BUF_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes
 constexpr int OUT_BUFS = 2;              // staging boxes per epilogue warp (TMA stores in flight)
+
 
 enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_POOL = 2 };
 
@@ -90,7 +90,7 @@ constexpr int num_stages() {
 }
 template <int kEpi>
 constexpr int epi_smem_bytes() {
-  return kEpi == EPI_POOL ? EPI_WARPS * 32 * TR_LD * 4 : EPI_WARPS * OUT_BUFS * OUT_BUF_BYTES;
+  return kEpi == EPI_POOL ? EPI_WARPS * 32 * 32 * 4 : EPI_WARPS * OUT_BUFS * OUT_BUF_BYTES;  // pool: dense 32x32 fp32 transpose tiles
 }
 template <int kEpi>
 constexpr int gemm_smem_bytes() {
@@ -145,62 +145,92 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int pit = 0;
-      for (int t = pair; t < total_tiles; t += n_pairs, ++pit) {
-        const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
-        const int m0 = (tt / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA;
-        const int n0 = (tt % p.n_tiles) * BN + static_cast<int>(rank) * BN_CTA;
-        const int kb0 = ks * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          const int tap = kb / p.cpt;
-          const int ch = kb - tap * p.cpt;
-          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-          if (kb == kb0) trace(p, pit, 0);
-          if (kb - kb0 < 8) trace(p, pit, 16 + kb - kb0);
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          uint8_t* sa = base + stage * STAGE_BYTES;
-          tma_load_2d_pair(sa, &tmA, leader_full, ch * BKE, m0 + tap_off_s[tap], p.pol_a);
-          tma_load_2d_pair(sa + A_BYTES, &tmB, leader_full, kb * BKE, n0, p.pol_b);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    // The whole warp runs the loop with warp-uniform control flow (addresses, coordinates, barrier state live in uniform
+    // registers); only expect_tx / TMA are predicated on one elected lane.
+    int stage = 0;
+    uint32_t phase = 0;
+    int pit = 0;
+    uint32_t rdy = 0;
+    uint32_t leader_full[STAGES];  // shared::cluster addresses of the leader's full barriers
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) leader_full[i] = mapa_u32(smem_u32(&full_bar[i]), 0);
+    for (int t = pair; t < total_tiles; t += n_pairs, ++pit) {
+      const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
+      const int m0 = (tt / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA;
+      const int n0 = (tt % p.n_tiles) * BN + static_cast<int>(rank) * BN_CTA;
+      const int kb0 = ks * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int tap = kb / p.cpt;
+        const int ch = kb - tap * p.cpt;
+        if (!rdy) mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+        if (kb == kb0 && lane == 0) trace(p, pit, 0);
+        const int arow = m0 + tap_off_s[tap];
+        int stage_n = stage + 1;
+        uint32_t phase_n = phase;
+        if (stage_n == STAGES) { stage_n = 0; phase_n ^= 1u; }
+        uint32_t lf = leader_full[0];
+#pragma unroll
+        for (int i = 1; i < STAGES; ++i) lf = (stage == i) ? leader_full[i] : lf;
+        const uint32_t sa = smem_u32(base + stage * STAGE_BYTES);
+        if (p.dbg & 8) {  // debug: no loads at all, only the barrier protocol
+          if (elect_one() && rank == 0) mbar_expect_tx(&full_bar[stage], 0);
+          __syncwarp();
+          rdy = 0;
+          stage = stage_n;
+          phase = phase_n;
+          continue;
         }
+        rdy = tma_step_pair(elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, smem_u32(&full_bar[stage]), lf, 2 * STAGE_BYTES, sa, &tmA,
+                            ch * BKE, arow, p.pol_a, sa + A_BYTES, &tmB, kb * BKE, n0, p.pol_b, smem_u32(&empty_bar[stage_n]),
+                            phase_n ^ 1u);
+        stage = stage_n;
+        phase = phase_n;
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
-    if (rank == 0 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform loop, one
+    // elected lane issues tcgen05.mma / tcgen05.commit; the readiness of the NEXT stage is probed before the MMAs are
+    // issued so the probe latency is off the critical path)
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      uint32_t rdy = 0;
       for (int t = pair; t < total_tiles; t += n_pairs, ++it) {
         const int buf = it & 1;
         const uint32_t use = (it >> 1) & 1;
-        trace(p, it, 1);
+        if (lane == 0) trace(p, it, 1);
         mbar_wait(&tempty_bar[buf], use ^ 1u, 2);  // both CTAs' epilogues have drained this accumulator buffer
-        tc_fence_after();
-        trace(p, it, 2);
+        if (lane == 0) trace(p, it, 2);
         const uint32_t d = tmem_base + buf * BN;
         const int kb0 = (t / mn_tiles) * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase, 3);
+          if (!(rdy & 1u)) mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
-          if (kb == kb0) trace(p, it, 3);
-          if (kb - kb0 < 8) trace(p, it, 24 + kb - kb0);
+          if (kb == kb0 && lane == 0) trace(p, it, 3);
           const uint32_t a_addr = smem_u32(base + stage * STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K inside the swizzle atom
-            umma_ss_pair<kTf32>(d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage], 0x3);  // smem slot free in both CTAs once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          int stage_n = stage + 1;
+          uint32_t phase_n = phase;
+          if (stage_n == STAGES) { stage_n = 0; phase_n ^= 1u; }
+          if (p.dbg & 16) {  // debug: no MMAs, only the barrier protocol
+            if (elect_one()) umma_commit_pair(&empty_bar[stage], 0x3);
+            __syncwarp();
+            rdy = 0;
+            stage = stage_n;
+            phase = phase_n;
+            continue;
+          }
+          rdy = umma_step_pair<kTf32>(elect_one() ? 1u : 0u, d, da, db, idesc, kb > kb0 ? 1u : 0u, STEP_COMMIT_A | STEP_PROBE_A,
+                                      smem_u32(&empty_bar[stage]), 0u, smem_u32(&full_bar[stage_n]), phase_n, 0u, 0u);
+          stage = stage_n;
+          phase = phase_n;
         }
-        umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
-        trace(p, it, 4);
+        if (elect_one()) umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
+        __syncwarp();
+        if (lane == 0) trace(p, it, 4);
       }
     }
   } else {
@@ -227,7 +257,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if constexpr (kEpi == EPI_POOL) {
         // per warp: 32 rows x 32 columns at a time, transposed through smem so that lane == column; column sums of
         // r = relu(acc + bias) and r^2 per utterance present in the 32-row block, packed f32x2 arithmetic.
-        float* tr = reinterpret_cast<float*>(epi_smem) + (warp - 2) * (32 * TR_LD);
+        float* tr = reinterpret_cast<float*>(epi_smem) + (warp - 2) * (32 * 32);  // dense 32x32, XOR-swizzled by 4-row groups
         const int my_u = (row < p.rows) ? __ldg(p.row_utt + row) : -1;
         const int slot0 = __ldg(p.blk_slot_base + (row0 >> 5));
         const unsigned valid = __ballot_sync(0xffffffffu, my_u >= 0);
@@ -237,13 +267,14 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld_32x32(tbase + c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tr[j * TR_LD + lane] = __uint_as_float(v[j]);  // tr[column][row]
+          for (int j = 0; j < 32; ++j)  // tr[column j][row lane], row group (lane/4) stored at slot (lane/4 ^ j%8)
+            tr[j * 32 + ((((lane >> 2) ^ (j & 7)) << 2) | (lane & 3))] = __uint_as_float(v[j]);
           __syncwarp();
           const int col = n0 + c + lane;  // this lane now owns one column
           const float b = (col < p.n && p.bias) ? __ldg(p.bias + col) : 0.f;
           float4 z[8];                    // the column's 32 rows
 #pragma unroll
-          for (int i = 0; i < 8; ++i) z[i] = *reinterpret_cast<const float4*>(tr + lane * TR_LD + 4 * i);
+          for (int i = 0; i < 8; ++i) z[i] = *reinterpret_cast<const float4*>(tr + lane * 32 + ((i ^ (lane & 7)) << 2));
           __syncwarp();
           const float2 b2 = make_float2(b, b);
           unsigned remaining = valid;

@@ -20,4 +20,4 @@ for cin in [int(v) for v in os.environ.get('KS','128,512').split(',')]:
     print(f"K={cin}: per tile stamps (cycles since first load issue): prod_first_load, mma_enter, mma_tempty_ok, mma_full0_ok, mma_commit_issued, epi_enter, epi_tfull_ok, epi_done")
     for it in range(4, 14):
         print(it, " ".join(f"{int(v - t0):7d}" for v in tr[it][:8]), "| epi rel tfull_ok:", " ".join(f"{int(v - tr[it][6]):6d}" for v in list(tr[it][8:11]) + list(tr[it][14:16]) + list(tr[it][11:14])), f"done {int(tr[it][7]-tr[it][6])}")
-        print("      load issue->ready per chunk:", " ".join(f"{int(tr[it][24+k]-tr[it][16+k]):6d}" for k in range(8)), "| mma ready gaps:", " ".join(f"{int(tr[it][24+k]-tr[it][24+k-1]):5d}" for k in range(1,8)))
+        print("      mma steps 4-7 [top, A ready, B ready, issued+committed] rel. to step-4 top:", " | ".join(" ".join(f"{int(tr[it][16+4*k+q]-tr[it][16]):5d}" for q in range(4)) for k in range(4)))
