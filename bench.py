@@ -30,6 +30,7 @@ N_UTTS = (N_UTTS // BATCH) * BATCH
 FLOPS_L = [122_880, 1_572_864, 1_572_864, 524_288, 1_536_000]  # per output frame, SURVEY §8d
 LOST = [4, 8, 14, 14, 14]
 SEG6_FLOPS = 3_072_000
+WORKLOAD = "c2: 1024 x 3 s utterances (300 x 24 MFCC), batch 256 per step and GPU, x_vec_extract_layer 6"
 
 
 def flops_per_utt(t):
@@ -108,7 +109,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "x-vectors/sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "frames_per_sec": v * FRAMES,
-            "config": {"workload": "c2: 1024 x 3 s utterances (300 x 24 MFCC), batch 256, x_vec_extract_layer 6"},
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "frames": FRAMES,
+                       "parallelism": "reference CPU implementation (oracle port), rank 0 only, all host threads"},
             "cpu_baseline": {"value": v, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{sample} of the {BATCH} utterances of a batch per step, oracle/xvector_oracle.extract_x_vec_t (fp32 torch CPU)"},
             "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -244,7 +246,7 @@ def run_b200(args, rank, world, local_rank):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if precision == "bf16" else "tf32", "data": "synthetic",
             "frames_per_sec": value * FRAMES,
-            "config": {"workload": "c2: 1024 x 3 s utterances (300 x 24 MFCC), batch 256 per step and GPU, x_vec_extract_layer 6",
+            "config": {"workload": WORKLOAD,
                        "global_batch": BATCH * world, "frames": FRAMES, "parallelism": f"utterance-sharded x{world}, no data-path collective",
                        "l2": f"inputs larger than L2: {n_res} distinct device-resident batches ({n_res * BATCH * FRAMES * CEPS * 4 >> 20} MiB) cycled; "
                              "2 batches in flight, activations of the two (4 x 78 MB) also exceed the 126 MB L2",
