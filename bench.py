@@ -283,7 +283,11 @@ def instrumented_layer_times(model, x_dev, lengths, n_batches, iters):
     names = ["tdnn1", "tdnn2", "tdnn3", "tdnn4", "tdnn5", "pool_finalize", "segment6"]
     acc = dict.fromkeys(names, 0.0)
     layers = list(model.time_context_layers)
-    plan = model._plan_for(lengths, 0)
+    lay = model._layout_for(lengths)
+    sc = model._scratch_for(0)
+    sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
+    part, pooled = sc.part[: lay.n_slots], sc.pooled[: lay.n_utts]
+    pooled_lp = None if sc.pooled_lp is None else sc.pooled_lp[: lay.n_utts]
     stack, (scale5, shift5) = model._stack_params()
     all_evs = []
     for it in range(iters + 2):  # no host sync inside: the launches queue up and run back to back on the device
@@ -293,15 +297,15 @@ def instrumented_layer_times(model, x_dev, lengths, n_batches, iters):
         for i, layer in enumerate(layers[:-1]):
             w, bias, offs = stack[i]
             h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True,
-                                    out=plan.act[i & 1][:, : layer.output_size], cin=layer.input_size)
+                                    out=sc.act[i & 1][: lay.rows, : layer.output_size], cin=layer.input_size)
             evs[i + 1].record()
         last = layers[-1]
         w, bias, offs = stack[-1]
-        ops.tdnn_pool_fused(h, w, last.output_size, offs, bias, plan.row_utt, plan.blk_slot_base, plan.part)
+        ops.tdnn_pool_fused(h, w, last.output_size, offs, bias, lay.row_utt, lay.blk_slot_base, part)
         evs[5].record()
-        ops.pool_finalize(plan.part, plan.utt_slot_start, plan.n_pool, last.output_size, scale5, shift5, out=plan.pooled, out_lp=plan.pooled_lp)
+        ops.pool_finalize(part, lay.utt_slot_start, lay.n_pool, last.output_size, scale5, shift5, out=pooled, out_lp=pooled_lp)
         evs[6].record()
-        model._head(plan.pooled, plan.pooled_lp, 6)
+        model._head(pooled, pooled_lp, 6)
         evs[7].record()
         all_evs.append(evs)
     torch.cuda.synchronize()

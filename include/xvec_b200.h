@@ -108,6 +108,12 @@ XVEC_API int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows
                          const float* bias_dev, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev,
                          float* part_dev, int64_t rows, void* stream);
 
+/* Expands per-utterance arrays (device, int32: first row, pooled-frame count, exclusive prefix sum of partial slots — see
+ * xvec_tdnn_pool_fused) into row_utt_dev (rows) and blk_slot_base_dev (ceil(rows/256)*8) on the device, so a ragged batch
+ * uploads 12 bytes per utterance instead of 4 bytes per frame.  The reference has no counterpart (fixed 3 s cuts, dataset.py:204). */
+XVEC_API int xvec_build_layout(const int32_t* starts_dev, const int32_t* n_pool_dev, const int32_t* slot_start_dev, int n_utts,
+                      int64_t rows, int32_t* row_utt_dev, int32_t* blk_slot_base_dev, void* stream);
+
 /* Standalone statistics pooling, first half (bandwidth-bound streaming reduction): for utterance u and chunk j,
  * column sums of x and x*x over rows [row_start[u] + j*XVEC_POOL_CHUNK, ...) -> part_dev[slot_start[u] + j][2][p].
  * replaces: the reads of torch.mean / torch.std in XVectorModel.stat_pool (main.py:59-63) on a materialised

@@ -32,6 +32,7 @@ _SIGNATURES = {
     "xvec_splitk_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
     "xvec_tdnn_pool_fused": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int, POINTER(c_int32), c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "xvec_build_layout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "xvec_stats_pool_partial": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                         c_void_p, c_void_p]),
     "xvec_pool_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

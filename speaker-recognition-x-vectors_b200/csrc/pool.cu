@@ -83,24 +83,20 @@ pool_finalize_kernel(const float* __restrict__ part, const int* __restrict__ slo
   const int sl0 = slot_start[u], sl1 = slot_start[u + 1];
   double S = 0.0, Q = 0.0;
   int sl = sl0;
-  for (; sl + 4 <= sl1; sl += 4) {  // 8 independent loads in flight, summed in slot order
-    float a[4], b[4];
+  for (; sl < sl1; sl += 12) {  // up to 24 independent loads in flight (a 3 s utterance has ~10 slots), summed in slot order
+    float a[12], b[12];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float* src = part + static_cast<size_t>(sl + i) * 2 * p + col;
-      a[i] = src[0];
-      b[i] = src[p];
+    for (int i = 0; i < 12; ++i) {
+      const bool ok = sl + i < sl1;
+      const float* src = part + static_cast<size_t>(ok ? sl + i : sl) * 2 * p + col;
+      a[i] = ok ? src[0] : 0.f;
+      b[i] = ok ? src[p] : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 12; ++i) {
       S += static_cast<double>(a[i]);
       Q += static_cast<double>(b[i]);
     }
-  }
-  for (; sl < sl1; ++sl) {
-    const float* src = part + static_cast<size_t>(sl) * 2 * p + col;
-    S += static_cast<double>(src[0]);
-    Q += static_cast<double>(src[p]);
   }
   const int n = n_rows[u];
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -123,6 +119,39 @@ pool_finalize_kernel(const float* __restrict__ part, const int* __restrict__ slo
       o[col] = m;
       o[p + col] = sd;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ layout expansion
+// Expands per-utterance arrays into the per-row / per-32-row-block bookkeeping of the fused pooling epilogue, on the device
+// (a ragged batch then only uploads 3 small per-utterance arrays instead of 4 bytes per frame).
+//   row_utt[r]        = u if row r is one of the first n_pool[u] rows of utterance u, else -1
+//   blk_slot_base[b]  = partial slot of the first utterance with a pooled row in 32-row block b
+__global__ void __launch_bounds__(256)
+build_layout_kernel(const int* __restrict__ starts, const int* __restrict__ n_pool, const int* __restrict__ slot_start, int n_utts,
+                    int rows, int n_blocks, int* __restrict__ row_utt, int* __restrict__ blk_slot_base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) {
+    int lo = 0, hi = n_utts - 1;  // last utterance with starts[u] <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (starts[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    row_utt[i] = (i - starts[lo] < n_pool[lo]) ? lo : -1;
+  }
+  if (i < n_blocks) {
+    const int first_row = i * XVEC_POOL_BLOCK;
+    int lo = 0, hi = n_utts;  // first utterance whose last pooled row is >= first_row
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (starts[mid] + n_pool[mid] - 1 >= first_row) hi = mid; else lo = mid + 1;
+    }
+    int base = 0;
+    if (lo < n_utts) {
+      const int b0 = starts[lo] / XVEC_POOL_BLOCK;
+      base = slot_start[lo] + (i > b0 ? i - b0 : 0);
+    }
+    blk_slot_base[i] = base;
   }
 }
 
@@ -203,6 +232,19 @@ static int check_launch(const char* what) {
 using namespace xvec;
 
 extern "C" {
+
+int xvec_build_layout(const int32_t* starts_dev, const int32_t* n_pool_dev, const int32_t* slot_start_dev, int n_utts, int64_t rows,
+                      int32_t* row_utt_dev, int32_t* blk_slot_base_dev, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!starts_dev || !n_pool_dev || !slot_start_dev || !row_utt_dev || !blk_slot_base_dev) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (n_utts <= 0 || rows <= 0 || rows > 0x7fffff00LL) return set_error(XVEC_E_ARG, "bad n_utts / rows");
+  const int n_blocks = static_cast<int>((rows + 255) / 256) * 8;
+  const long long n = rows > n_blocks ? rows : n_blocks;
+  build_layout_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      starts_dev, n_pool_dev, slot_start_dev, n_utts, static_cast<int>(rows), n_blocks, row_utt_dev, blk_slot_base_dev);
+  return check_launch("build_layout_kernel");
+}
 
 int xvec_stats_pool_partial(const void* x_dev, int x_dtype, int64_t x_ld, int p, const int64_t* row_start_dev,
                             const int32_t* n_rows_dev, const int32_t* slot_start_dev, int n_utts, int max_chunks, float* part_dev,

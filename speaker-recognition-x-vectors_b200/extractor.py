@@ -11,7 +11,6 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from .layout import bucket_batches
 
 
 @dataclass
@@ -33,6 +32,7 @@ class HostExtractor:
         with torch.cuda.device(self.device):
             self.slots = [_Slot(torch.cuda.Stream(), torch.cuda.Event()) for _ in range(n_slots)]
         self._next = 0
+        self._flat = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -75,30 +75,43 @@ class HostExtractor:
         sl.busy = False
         return sl.out_host[: sl.n_out]
 
-    def extract_all(self, utts, max_frames: int = 1 << 17, max_utts: int = 1024) -> np.ndarray:
-        """Extract a whole (ragged) list of host (T_i, C) float32 tensors: length-bucketed batches, double-buffered.
+    def extract_flat(self, flat_host: torch.Tensor, lengths, max_frames: int = 1 << 17, max_utts: int = 1 << 30) -> np.ndarray:
+        """Extract a whole (ragged) set given as ONE flat host tensor (sum(lengths), C) float32 (pinned for full speed) plus
+        the utterance lengths.  Batches are runs of CONSECUTIVE utterances of at most max_frames frames: the flat frame
+        layout has no padding, so there is nothing to gain from length bucketing and no per-batch gather is needed.
         Returns float64 (N, dim) in the original order, the dtype test_epoch_end stores (main.py:145)."""
-        lengths = np.asarray([int(u.shape[0]) for u in utts], dtype=np.int64)
+        lengths = np.asarray(lengths, dtype=np.int64)
+        if flat_host.dim() != 2 or flat_host.shape[0] != int(lengths.sum()):
+            raise ValueError("flat_host must be (sum(lengths), C)")
+        ends = np.cumsum(lengths)
         out = None
         pending = []
 
         def drain(k):
             nonlocal out
             while len(pending) > k:
-                ticket, idx = pending.pop(0)
+                ticket, lo, hi = pending.pop(0)
                 r = self.result(ticket).numpy()
                 if out is None:
-                    out = np.empty((len(utts), r.shape[1]), dtype=np.float64)
-                out[idx] = r
+                    out = np.empty((len(lengths), r.shape[1]), dtype=np.float64)
+                out[lo:hi] = r
 
-        stage = [None] * len(self.slots)
-        for idx in bucket_batches(lengths, max_frames, max_utts):
+        lo = 0
+        n = len(lengths)
+        while lo < n:
+            row0 = int(ends[lo - 1]) if lo else 0
+            hi = int(np.searchsorted(ends, row0 + max_frames, side="right"))
+            hi = max(lo + 1, min(hi, lo + max_utts, n))
             drain(len(self.slots) - 1)
-            rows = int(lengths[idx].sum())
-            k = self._next
-            if stage[k] is None or stage[k].shape[0] < rows:
-                stage[k] = torch.empty((max(rows, max_frames), utts[0].shape[1]), dtype=torch.float32, pin_memory=True)
-            torch.cat([utts[i] for i in idx], out=stage[k][:rows])
-            pending.append((self.submit(stage[k][:rows], lengths[idx]), idx))
+            pending.append((self.submit(flat_host[row0:int(ends[hi - 1])], lengths[lo:hi]), lo, hi))
+            lo = hi
         drain(0)
         return out
+
+    def extract_all(self, utts, max_frames: int = 1 << 17, max_utts: int = 1 << 30) -> np.ndarray:
+        """Extract a list of host (T_i, C) float32 tensors: concatenated once into a pinned flat buffer, then extract_flat."""
+        rows = sum(int(u.shape[0]) for u in utts)
+        if self._flat is None or self._flat.shape[0] < rows or self._flat.shape[1] != utts[0].shape[1]:
+            self._flat = torch.empty((rows, utts[0].shape[1]), dtype=torch.float32, pin_memory=True)
+        torch.cat([u.float() if u.dtype != torch.float32 else u for u in utts], out=self._flat[:rows])
+        return self.extract_flat(self._flat[:rows], [int(u.shape[0]) for u in utts], max_frames, max_utts)

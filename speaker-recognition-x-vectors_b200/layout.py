@@ -61,6 +61,25 @@ def build_layout(lengths, lost_frames: int = TOTAL_CONTEXT) -> FrameLayout:
     return FrameLayout(lengths, starts, n_pool.astype(np.int32), rows, row_utt, blk_slot_base, utt_slot_start.astype(np.int32), n_slots)
 
 
+def utterance_layout(lengths, lost_frames: int = TOTAL_CONTEXT):
+    """Per-utterance part of build_layout only (O(#utterances) host work): int32 arrays (starts, n_pool, utt_slot_start),
+    total rows and slots.  The per-row / per-block arrays are expanded from these on the device (xvec_build_layout)."""
+    lengths = np.asarray(lengths, dtype=np.int64).reshape(-1)
+    if lengths.size == 0:
+        raise ValueError("empty batch")
+    if (lengths <= lost_frames).any():
+        raise ValueError(f"every utterance needs more than {lost_frames} frames (the TDNN context); got min {int(lengths.min())}")
+    starts = np.concatenate(([0], np.cumsum(lengths)[:-1]))
+    rows = int(lengths.sum())
+    if rows >= 2**31 - 256:
+        raise ValueError("batch too large for 32-bit row indices; split it")
+    n_pool = lengths - lost_frames
+    blk = _lib.POOL_BLOCK
+    cnt = (starts + n_pool - 1) // blk - starts // blk + 1
+    slot_start = np.concatenate(([0], np.cumsum(cnt)))
+    return starts.astype(np.int32), n_pool.astype(np.int32), slot_start.astype(np.int32), rows, int(slot_start[-1])
+
+
 def lpt_partition(lengths, n_parts: int, lost_frames: int = TOTAL_CONTEXT):
     """Longest-processing-time-first partition of utterances over `n_parts` workers by pooled frames.
 

@@ -124,6 +124,20 @@ def pool_finalize(part: torch.Tensor, slot_start: torch.Tensor, n_rows: torch.Te
     return out
 
 
+def build_layout_device(starts: torch.Tensor, n_pool: torch.Tensor, slot_start: torch.Tensor, rows: int, row_utt: torch.Tensor,
+                        blk_slot_base: torch.Tensor) -> None:
+    """Expand per-utterance int32 device arrays into row_utt (rows) / blk_slot_base (ceil(rows/256)*8) on the device."""
+    _require_cuda(starts, n_pool, slot_start, row_utt, blk_slot_base)
+    lib = _lib.load()
+    if any(t.dtype != torch.int32 or not t.is_contiguous() for t in (starts, n_pool, slot_start, row_utt, blk_slot_base)):
+        raise ValueError("layout arrays must be contiguous int32")
+    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * 8 or slot_start.numel() < starts.numel() + 1:
+        raise ValueError("layout output arrays are too small")
+    with torch.cuda.device(starts.device):
+        check(lib.xvec_build_layout(ptr(starts), ptr(n_pool), ptr(slot_start), starts.numel(), rows, ptr(row_utt), ptr(blk_slot_base),
+                                    stream_ptr()))
+
+
 def stats_pool_ragged(x: torch.Tensor, row_start: np.ndarray, n_rows: np.ndarray, out_lp: torch.Tensor | None = None):
     """Standalone statistics pooling over row ranges of a flat (rows, p) matrix -> float32 (n_utts, 2p)."""
     _require_cuda(x)

@@ -19,28 +19,79 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layout import FrameLayout, build_layout
+from .layout import utterance_layout
 from .tdnn_layer import TdnnLayer, _aligned_rows, tap_offsets
 
 PRECISIONS = {"tf32": torch.float32, "fp32": torch.float32, "bf16": torch.bfloat16}
 
 
-class _Plan:
-    """Device-side bookkeeping + scratch for one batch layout (reused across calls with the same lengths)."""
+class _Layout:
+    """Device-side pooling bookkeeping of one batch layout (cached by lengths for repeated shapes)."""
 
-    def __init__(self, layout: FrameLayout, device, act_dtype, widths, pool_dim):
-        self.layout = layout
-        self.row_utt = torch.from_numpy(layout.row_utt).to(device)
-        self.blk_slot_base = torch.from_numpy(layout.blk_slot_base).to(device)
-        self.utt_slot_start = torch.from_numpy(layout.utt_slot_start).to(device)
-        self.n_pool = torch.from_numpy(layout.n_pool).to(device)
+    def __init__(self, lengths, lost_frames, device, staging):
+        starts, n_pool, slot_start, rows, n_slots = utterance_layout(lengths, lost_frames)
+        self.rows, self.n_slots, self.n_utts = rows, n_slots, int(starts.shape[0])
+        u = self.n_utts
+        host = staging.get(3 * u + 1)  # pinned, reused: one upload of 12 bytes per utterance
+        host[:u] = torch.from_numpy(starts)
+        host[u:2 * u] = torch.from_numpy(n_pool)
+        host[2 * u:3 * u + 1] = torch.from_numpy(slot_start)
+        dev = torch.empty(3 * u + 1, dtype=torch.int32, device=device)
+        dev.copy_(host[: 3 * u + 1], non_blocking=True)
+        staging.mark()
+        self.starts, self.n_pool, self.utt_slot_start = dev[:u], dev[u:2 * u], dev[2 * u:]
+        self.row_utt = torch.empty(rows, dtype=torch.int32, device=device)
+        self.blk_slot_base = torch.empty(((rows + 255) // 256) * 8, dtype=torch.int32, device=device)
+        ops.build_layout_device(self.starts, self.n_pool, self.utt_slot_start, rows, self.row_utt, self.blk_slot_base)
+
+
+class _PinnedStaging:
+    """A small ring of reusable pinned int32 buffers for the per-batch layout uploads; an event per buffer guards reuse, so
+    the host only ever waits for a copy issued 16 batches ago."""
+
+    RING = 16
+
+    def __init__(self):
+        self.bufs = [None] * self.RING
+        self.evs = [None] * self.RING
+        self.i = -1
+
+    def get(self, n):
+        self.i = (self.i + 1) % self.RING
+        if self.evs[self.i] is not None:
+            self.evs[self.i].synchronize()
+        if self.bufs[self.i] is None or self.bufs[self.i].numel() < n:
+            self.bufs[self.i] = torch.empty(max(n, 8192), dtype=torch.int32, pin_memory=True)
+        return self.bufs[self.i]
+
+    def mark(self):
+        if self.evs[self.i] is None:
+            self.evs[self.i] = torch.cuda.Event()
+        self.evs[self.i].record()
+
+
+class _Scratch:
+    """Activation ping-pong buffers, pooling partials and pooled statistics of one slot; grown on demand, shared by layouts."""
+
+    def __init__(self, device, act_dtype, widths, pool_dim):
+        self.device, self.act_dtype, self.pool_dim = device, act_dtype, pool_dim
         per16 = 16 // torch.empty((), dtype=act_dtype).element_size()
-        ld = (max(widths) + per16 - 1) // per16 * per16
-        self.act = [torch.empty((layout.rows, ld), dtype=act_dtype, device=device) for _ in range(2)]
-        self.part = torch.empty((layout.n_slots, 2, pool_dim), dtype=torch.float32, device=device)
-        self.pooled = torch.empty((layout.n_utts, 2 * pool_dim), dtype=torch.float32, device=device)
-        self.pooled_lp = (torch.empty((layout.n_utts, 2 * pool_dim), dtype=act_dtype, device=device)
-                          if act_dtype != torch.float32 else None)
+        self.ld = (max(widths) + per16 - 1) // per16 * per16
+        self.rows_cap = self.slots_cap = self.utts_cap = 0
+        self.act = self.part = self.pooled = self.pooled_lp = None
+
+    def ensure(self, rows, n_slots, n_utts):
+        if rows > self.rows_cap:
+            self.rows_cap = max(rows, int(self.rows_cap * 1.25))
+            self.act = [torch.empty((self.rows_cap, self.ld), dtype=self.act_dtype, device=self.device) for _ in range(2)]
+        if n_slots > self.slots_cap:
+            self.slots_cap = max(n_slots, int(self.slots_cap * 1.25))
+            self.part = torch.empty((self.slots_cap, 2, self.pool_dim), dtype=torch.float32, device=self.device)
+        if n_utts > self.utts_cap:
+            self.utts_cap = max(n_utts, int(self.utts_cap * 1.25))
+            self.pooled = torch.empty((self.utts_cap, 2 * self.pool_dim), dtype=torch.float32, device=self.device)
+            self.pooled_lp = (torch.empty((self.utts_cap, 2 * self.pool_dim), dtype=self.act_dtype, device=self.device)
+                              if self.act_dtype != torch.float32 else None)
 
 
 class XVectorModel(nn.Module):
@@ -66,7 +117,8 @@ class XVectorModel(nn.Module):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
         self.precision = precision
-        self._plans: "OrderedDict[tuple, _Plan]" = OrderedDict()
+        self._layouts: "OrderedDict[tuple, _Layout]" = OrderedDict()
+        self._scratch = {}
         self._fc_prep = {}
 
     # ------------------------------------------------------------------ helpers
@@ -85,21 +137,30 @@ class XVectorModel(nn.Module):
         if self.training:
             raise RuntimeError("xvec_b200.XVectorModel implements the eval-mode extraction path only; call .eval() first")
 
-    def _plan_for(self, lengths, slot: int = 0) -> _Plan:
+    def _layout_for(self, lengths) -> _Layout:
         lengths = np.asarray(lengths, dtype=np.int64)
         dev = self._device()
-        key = (lengths.tobytes(), str(dev), self.precision, slot)
-        plan = self._plans.get(key)
-        if plan is None:
-            layers = list(self.time_context_layers)
-            widths = [l.output_size for l in layers[:-1]]
-            plan = _Plan(build_layout(lengths, self.lost_frames), dev, self.act_dtype, widths, layers[-1].output_size)
-            self._plans[key] = plan
-            while len(self._plans) > 16:
-                self._plans.popitem(last=False)
+        key = (lengths.tobytes(), str(dev), torch.cuda.current_stream().cuda_stream)
+        lay = self._layouts.get(key)
+        if lay is None:
+            st = self._scratch.setdefault(("pin", key[2]), _PinnedStaging())
+            lay = _Layout(lengths, self.lost_frames, dev, st)
+            self._layouts[key] = lay
+            while len(self._layouts) > 128:
+                self._layouts.popitem(last=False)
         else:
-            self._plans.move_to_end(key)
-        return plan
+            self._layouts.move_to_end(key)
+        return lay
+
+    def _scratch_for(self, slot: int) -> _Scratch:
+        dev = self._device()
+        key = (str(dev), self.precision, slot)
+        sc = self._scratch.get(key)
+        if sc is None:
+            layers = list(self.time_context_layers)
+            sc = _Scratch(dev, self.act_dtype, [l.output_size for l in layers[:-1]], layers[-1].output_size)
+            self._scratch[key] = sc
+        return sc
 
     def _stack_params(self):
         """Packed operands of the five TDNN layers for the fused pipeline, with every layer's eval-mode BatchNorm folded
@@ -161,9 +222,11 @@ class XVectorModel(nn.Module):
             raise ValueError("xvec_b200 has no CPU path: move the input (and the model) to a CUDA device")
         if flat_x.dim() != 2 or flat_x.shape[1] != self.input_size:
             raise ValueError(f"expected a flat (rows, {self.input_size}) frame matrix")
-        plan = self._plan_for(lengths, slot)
-        if plan.layout.rows != flat_x.shape[0]:
+        lay = self._layout_for(lengths)
+        if lay.rows != flat_x.shape[0]:
             raise ValueError("sum(lengths) does not match the number of rows")
+        sc = self._scratch_for(slot)
+        sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
         layers = list(self.time_context_layers)
         if flat_x.dtype != torch.float32:
             flat_x = flat_x.float()
@@ -171,14 +234,17 @@ class XVectorModel(nn.Module):
         h = _aligned_rows(flat_x)  # layer 1 always reads float32 frames (TF32 math): no cast pass over the input
         for i, layer in enumerate(layers[:-1]):
             w, bias, offs = stack[i]
-            out = plan.act[i & 1][:, : layer.output_size]
+            out = sc.act[i & 1][: lay.rows, : layer.output_size]
             h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True, out=out, cin=layer.input_size)
         last = layers[-1]
         w, bias, offs = stack[-1]
-        ops.tdnn_pool_fused(h, w, last.output_size, offs, bias, plan.row_utt, plan.blk_slot_base, plan.part)
-        ops.pool_finalize(plan.part, plan.utt_slot_start, plan.n_pool, last.output_size, scale5, shift5, out=plan.pooled,
-                          out_lp=plan.pooled_lp)
-        return plan.pooled, plan.pooled_lp
+        part = sc.part[: lay.n_slots]
+        pooled = sc.pooled[: lay.n_utts]
+        pooled_lp = None if sc.pooled_lp is None else sc.pooled_lp[: lay.n_utts]
+        ops.tdnn_pool_fused(h, w, last.output_size, offs, bias, lay.row_utt, lay.blk_slot_base, part)
+        ops.pool_finalize(part, lay.utt_slot_start, lay.n_pool, last.output_size, scale5, shift5, out=pooled, out_lp=pooled_lp)
+        return pooled, pooled_lp
+
 
     def _head(self, pooled, pooled_lp, layer) -> torch.Tensor:
         a = pooled if pooled_lp is None else pooled_lp
