@@ -258,7 +258,8 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks,
             "wall_ms_per_step": t_wall / args.steps * 1e3,
             "roofline": {"kernel": "tdnn_gemm_kernel (5 launches/step: TDNN1-4 store epilogue, TDNN5 fused pooling epilogue)",
-                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": 100463616 if precision == "bf16" else None,  # dram bytes read+write of one TDNN2 launch (ncu, profiles/r01_v5_ncu_full_summary.txt)
                          "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops_sustained" + ("" if precision == "bf16" else " / 2 (TF32)"),
                          "frac_of_burst_peak": achieved / (peaks["bf16_tflops"] if precision == "bf16" else peaks["bf16_tflops"] / 2),
                          "algorithmic_flops_per_step": tdnn_flops, "ms_per_step": tdnn_ms},
@@ -333,7 +334,8 @@ def pooling_roofline(model, dev, peaks):
     gbs = nbytes / (ms / 1e3) / 1e9
     del a
     return {"kernel": "stats_pool_partial_kernel + pool_finalize_kernel (standalone stat_pool, 64 x 5986 x 1500 fp32)", "bound": "hbm",
-            "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+            "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "traffic": 2441932472,  # dram__bytes_read+write of stats_pool_partial_kernel per launch, profiles/r01_v5_ncu_pool_summary.txt
             "algorithmic_bytes": nbytes, "ms": ms, "peak_source": f"{peaks['source']} MEASURED_PEAKS.json hbm_gbs"}
 
 

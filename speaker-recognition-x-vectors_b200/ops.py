@@ -11,6 +11,9 @@ from . import _lib
 from ._lib import BF16, F32, check, dtype_code, ptr, stream_ptr, taps_array
 
 
+_POOL_LAYOUTS = {}
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -150,16 +153,22 @@ def stats_pool_ragged(x: torch.Tensor, row_start: np.ndarray, n_rows: np.ndarray
         raise ValueError("every utterance needs at least one frame to pool")
     if (row_start < 0).any() or ((row_start + n_rows) > x.shape[0]).any():
         raise ValueError("row range outside of x")
-    chunks = (n_rows.astype(np.int64) + _lib.POOL_CHUNK - 1) // _lib.POOL_CHUNK
-    slot_start = np.concatenate(([0], np.cumsum(chunks))).astype(np.int32)
     dev = x.device
-    rs_d = torch.from_numpy(row_start).to(dev)
-    nr_d = torch.from_numpy(n_rows).to(dev)
-    ss_d = torch.from_numpy(slot_start).to(dev)
-    part = torch.empty((int(slot_start[-1]), 2, p), dtype=torch.float32, device=dev)
+    key = (row_start.tobytes(), n_rows.tobytes(), str(dev))
+    hit = _POOL_LAYOUTS.get(key)
+    if hit is None:  # small index arrays: uploaded once per distinct (row_start, n_rows) and cached
+        chunks = (n_rows.astype(np.int64) + _lib.POOL_CHUNK - 1) // _lib.POOL_CHUNK
+        slot_start = np.concatenate(([0], np.cumsum(chunks))).astype(np.int32)
+        hit = (torch.from_numpy(row_start).to(dev), torch.from_numpy(n_rows).to(dev), torch.from_numpy(slot_start).to(dev),
+               int(slot_start[-1]), int(chunks.max()))
+        if len(_POOL_LAYOUTS) >= 8:
+            _POOL_LAYOUTS.pop(next(iter(_POOL_LAYOUTS)))
+        _POOL_LAYOUTS[key] = hit
+    rs_d, nr_d, ss_d, n_slots, max_chunks = hit
+    part = torch.empty((n_slots, 2, p), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib.xvec_stats_pool_partial(ptr(x), dtype_code(x.dtype), ld, p, ptr(rs_d), ptr(nr_d), ptr(ss_d), len(n_rows),
-                                          int(chunks.max()), ptr(part), stream_ptr()))
+                                          max_chunks, ptr(part), stream_ptr()))
     return pool_finalize(part, ss_d, nr_d, p, out_lp=out_lp)
 
 
