@@ -32,13 +32,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """debug=True builds libxvec_b200_debug.so with -DXVEC_DEBUG (per-tile clock stamps and epilogue/mainloop skip switches
+    for tools/trace_tiles.py etc.; select it with XVEC_LIB=...)."""
+    if debug:
+        return _build_to(os.path.join(HERE, "libxvec_b200_debug.so"), list(NVCC_FLAGS) + ["-DXVEC_DEBUG"], verbose, "_dbg")
     if not force and not needs_build():
         return LIB
-    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if verbose else [])
+    return _build_to(LIB, list(NVCC_FLAGS), verbose, "")
+
+
+def _build_to(lib: str, flags, verbose: bool, suffix: str) -> str:
+    flags = flags + (["-Xptxas", "-v"] if verbose else [])
     objs = []
     for s in SOURCES:
-        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, s.replace(".cu", suffix + ".o"))
         cmd = [_nvcc()] + flags + ["-c", os.path.join(CSRC, s), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
@@ -46,13 +54,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode:
             raise RuntimeError(f"nvcc failed on {s}")
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", lib] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, debug="--debug" in sys.argv))

@@ -78,11 +78,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return r;
 }
 
+// Developer instrumentation (tools/trace_tiles.py, tools/episweep.py): only in -DXVEC_DEBUG builds
+// (build.py --debug -> libxvec_b200_debug.so); the product library compiles all of it out.
 constexpr int TRACE_TILES = 32;
 constexpr int TRACE_SLOTS = 32;
+#ifdef XVEC_DEBUG
 __device__ __forceinline__ void trace(const GemmParams& p, int it, int slot) {
   if (p.trace && blockIdx.x == 0 && it < TRACE_TILES) p.trace[it * TRACE_SLOTS + slot] = clock64();
 }
+#define XVEC_DBG(p, bit) ((p).dbg & (bit))
+#else
+__device__ __forceinline__ void trace(const GemmParams&, int, int) {}
+#define XVEC_DBG(p, bit) 0
+#endif
 
 template <int kEpi>
 constexpr int num_stages() {
@@ -172,7 +180,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int i = 1; i < STAGES; ++i) lf = (stage == i) ? leader_full[i] : lf;
         const uint32_t sa = smem_u32(base + stage * STAGE_BYTES);
-        if (p.dbg & 8) {  // debug: no loads at all, only the barrier protocol
+        if (XVEC_DBG(p, 8)) {  // debug: no loads at all, only the barrier protocol
           if (elect_one() && rank == 0) mbar_expect_tx(&full_bar[stage], 0);
           __syncwarp();
           rdy = 0;
@@ -215,7 +223,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           int stage_n = stage + 1;
           uint32_t phase_n = phase;
           if (stage_n == STAGES) { stage_n = 0; phase_n ^= 1u; }
-          if (p.dbg & 16) {  // debug: no MMAs, only the barrier protocol
+          if (XVEC_DBG(p, 16)) {  // debug: no MMAs, only the barrier protocol
             if (elect_one()) umma_commit_pair(&empty_bar[stage], 0x3);
             __syncwarp();
             rdy = 0;
@@ -327,7 +335,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr int CHUNKS = GROUP_COLS / 32;      // tcgen05.ld chunks per box
         for (int c = cbeg; c < cend && n0 + c < p.n; c += GROUP_COLS) {
           uint8_t* ob = out_stage + (store_seq % OUT_BUFS) * OUT_BUF_BYTES;
-          if (p.vec_store && !(p.dbg & 2)) {
+          if (p.vec_store && !(XVEC_DBG(p, 2))) {
             if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();  // the store that last used this box has read it
             __syncwarp();
           }
@@ -336,7 +344,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int col0 = n0 + c + cc * 32;
             if (col0 >= p.n) break;  // warp-uniform; the box is clipped by TMA
             uint32_t v[32];
-            if (!(p.dbg & 1)) {
+            if (!(XVEC_DBG(p, 1))) {
               if (warp == 2 && lane == 0 && c == cbeg && cc == 0) trace(p, it, 8);
               tmem_ld_32x32(tbase + c + cc * 32, v);
               tmem_ld_wait();
@@ -378,7 +386,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             const bool cvt_relu = p.relu && p.scale == nullptr;  // ReLU not applied yet (bf16 fast path)
             if (warp == 2 && lane == 0 && c == cbeg && cc == 0) trace(p, it, 10);
-            if (p.dbg & 2) {
+            if (XVEC_DBG(p, 2)) {
               if (o[0] == 123.456f && o[31] == 1.f) ob[lane] = 1;
             } else if (p.vec_store) {
               // row `lane` of the box, 16-byte pieces XOR-swizzled like CU_TENSOR_MAP_SWIZZLE_128B expects
@@ -422,7 +430,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          if (p.vec_store && !(p.dbg & 2)) {
+          if (p.vec_store && !(XVEC_DBG(p, 2))) {
             if (warp == 2 && lane == 0 && c == cbeg) trace(p, it, 14);
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();

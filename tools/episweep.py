@@ -1,4 +1,5 @@
 import sys, os
+# the XVEC_DBG skip switches exist only in the debug library: python speaker-recognition-x-vectors_b200/build.py --debug; XVEC_LIB=.../libxvec_b200_debug.so
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, xvec_b200
 from xvec_b200 import ops

@@ -1,5 +1,9 @@
 import sys, os
 os.environ["XVEC_TRACE"] = "1"
+import importlib
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+importlib.import_module("speaker-recognition-x-vectors_b200.build").build(debug=True)  # -DXVEC_DEBUG variant with the trace stamps
+os.environ.setdefault("XVEC_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "speaker-recognition-x-vectors_b200", "libxvec_b200_debug.so"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes, numpy as np, torch, xvec_b200
 from xvec_b200 import ops
