@@ -9,10 +9,10 @@ from .layout import build_layout, bucket_batches, lpt_partition  # noqa: F401
 from .tdnn_layer import TdnnLayer, get_time_context, tap_offsets  # noqa: F401
 from .xvector import XVectorModel  # noqa: F401
 from .extractor import HostExtractor  # noqa: F401
-from . import io_csv, sharding  # noqa: F401
+from . import io_csv, scoring, sharding  # noqa: F401
 from .io_csv import read_xvector_csv, write_xvector_csv  # noqa: F401
 
 TDNN = TdnnLayer  # BASELINE.json's north_star calls the layer "TDNN"
 
 __all__ = ["TdnnLayer", "TDNN", "XVectorModel", "get_time_context", "tap_offsets", "build_layout", "bucket_batches",
-           "lpt_partition", "ops", "layout", "HostExtractor", "io_csv", "sharding", "read_xvector_csv", "write_xvector_csv"]
+           "lpt_partition", "ops", "layout", "HostExtractor", "io_csv", "scoring", "sharding", "read_xvector_csv", "write_xvector_csv"]

@@ -141,3 +141,25 @@ def test_trial_decisions_identical(xb, state_dict):
         s = xb.ops.cosine_trials(xv, torch.from_numpy(enrol).int().cuda(), torch.from_numpy(test).int().cuda(), center=True).cpu().numpy()
         assert np.abs(s - s_ref).max() < margin, (precision, np.abs(s - s_ref).max(), margin)
         assert np.array_equal(s >= thr, s_ref >= thr)
+
+
+def test_scoring_module_trial_file(xb, state_dict):
+    """Product scoring path: trial file -> GPU centred cosine -> EER / minDCF, against fp64 numpy on the same embeddings."""
+    from xvec_b200 import scoring
+    n, nspk = 60, 6
+    lens = ox.synth_lengths(n, 60, 200, seed=8)
+    utts = ox.synth_speaker_utts(lens, nspk, seed=9)
+    m = _model(xb, state_dict, "tf32")
+    xv = m.extract_x_vec_flat(torch.cat(utts).cuda(), lens)
+    ids = [f"id{10000 + i % nspk}/vid{i}/00001.wav" for i in range(n)]
+    enrol, test, target = ox.synth_trials(n, 400, n_speakers=nspk, seed=2)
+    lines = [f"{int(t)} {ids[e]} {ids[k]}\n" for e, k, t in zip(enrol, test, target)]
+    s, tgt = scoring.score_trial_file(xv, ids, lines)
+    assert np.array_equal(tgt, target)
+    ref = ox.cosine_scores_np(xv.double().cpu().numpy(), enrol, test, center=True)
+    assert np.abs(s - ref).max() < 1e-5
+    e, thr = scoring.eer(s, tgt)
+    d, _ = scoring.min_dcf(s, tgt)
+    assert 0.0 <= d <= e + 1e-9 <= 0.5
+    with pytest.raises(ValueError):
+        scoring.score_trial_file(xv, ids, ["1 nope/a/b.wav " + ids[0] + "\n"])

@@ -91,3 +91,30 @@ def test_sharded_extraction_world2_gloo():
     utts = list(torch.split(torch.randn(int(lens.sum()), 24, generator=g), [int(v) for v in lens]))
     assert np.array_equal(out0, _fake_extract(utts))                                   # original order restored
     assert np.array_equal(sharding.extract_sharded(utts, _fake_extract), out0)         # world == 1 path
+
+
+def test_eer_and_min_dcf_from_first_principles():
+    from xvec_b200 import scoring
+    rng = np.random.default_rng(0)
+    tar = rng.normal(1.0, 1.0, 4000)
+    non = rng.normal(-1.0, 1.0, 6000)
+    s = np.concatenate([tar, non])
+    t = np.concatenate([np.ones(4000, bool), np.zeros(6000, bool)])
+    e, thr = scoring.eer(s, t)
+    far = (non >= thr).mean()
+    frr = (tar < thr).mean()
+    assert abs(far - frr) < 2e-3 and abs(e - 0.5 * (far + frr)) < 1e-12
+    assert abs(e - 0.1587) < 0.01                          # Phi(-1) for unit-variance classes 2 sigma apart
+    d, thr_d = scoring.min_dcf(s, t, p_target=0.5)
+    assert abs(d - 0.5 * ((tar < thr_d).mean() + (non >= thr_d).mean())) < 1e-12
+    assert d <= 0.5 * (far + frr) + 1e-12 and abs(d - 0.1587) < 0.01
+    # brute force over every candidate threshold
+    cands = np.sort(s)
+    brute = min(0.5 * ((tar < c).mean() + (non >= c).mean()) for c in cands[::50])
+    assert d <= brute + 1e-12
+    # the oracle's EER threshold agrees on decisions up to ties
+    from oracle import xvector_oracle as ox
+    e2, thr2, _ = ox.eer_threshold_np(s, t)
+    assert abs(e - e2) < 2e-3
+    with pytest.raises(ValueError):
+        scoring.eer(np.zeros(4), np.ones(4, bool))
