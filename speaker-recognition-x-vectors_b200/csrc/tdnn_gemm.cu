@@ -9,15 +9,19 @@
 //
 // One output tile = 256 frames x 256 channels, computed by a CTA PAIR (cluster of 2, tcgen05 cta_group::2): each CTA
 // stages its own 128 frame rows (A) and HALF of the weight tile (B, 128 channels) per 128-byte K chunk, so a CTA moves
-// 32 KiB through shared memory per 128x256x{64 bf16|32 tf32} of its MMA work instead of 48 KiB — v1 of this kernel
-// (single-CTA 128x256 tiles) was bound by shared-memory bandwidth (TMA writes + UMMA operand reads), see DESIGN.md.
+// 32 KiB through shared memory per 128x256x{64 bf16|32 tf32} of its MMA work instead of the 48 KiB of a single-CTA
+// 128x256 tile (measurements and the alternatives that were tried are in DESIGN.md §3).
 //
 // Persistent, warp-specialised CTA (320 threads, 1 CTA/SM, 74 pairs):
 //   warp 0      TMA producer (both CTAs; completion bytes of both land on the LEADER's full barrier)
-//   warp 1      TMEM owner; in the leader CTA one thread issues tcgen05.mma.cta_group::2 (UMMA 256x256xK, fp32
-//               accumulators in TMEM, two 256-column buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2-9   epilogue (both CTAs, 128 rows each; 2 warps per TMEM lane quarter, each half of the columns): tcgen05.ld -> bias/ReLU/BatchNorm affine -> 128B-swizzled smem
-//               staging -> TMA store                                                          (EPI_STORE_*)
+//   warp 1      TMEM owner; in the leader CTA it issues tcgen05.mma.cta_group::2 (UMMA 256x256xK, fp32 accumulators in
+//               TMEM, two 256-column buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
+//               Both run warp-uniform loops (addresses / descriptors stay in uniform registers) and predicate only the
+//               single-thread instructions on one elected lane; each step first probes the NEXT stage's barrier so the
+//               probe latency overlaps the TMA / MMA issue (ptx.cuh: tma_step_pair, umma_step_pair).
+//   warps 2-9   epilogue (both CTAs, 128 rows each; 2 warps per TMEM lane quarter, each half of the columns):
+//               tcgen05.ld -> bias/ReLU (packed f32x2, cvt.relu) / BatchNorm affine -> 128B-swizzled smem staging
+//               -> TMA store                                                                  (EPI_STORE_*)
 //               or -> per-utterance column sums of r and r^2 (statistics pooling partials)    (EPI_POOL)
 #include "ptx.cuh"
 #include "xvec_internal.h"
