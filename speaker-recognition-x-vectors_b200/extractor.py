@@ -2,7 +2,8 @@
 test_step/test_epoch_end (main.py:135-146) makes, minus the per-utterance .cpu() round trips.
 
 Each of the `n_slots` slots owns a CUDA stream, a device staging buffer, model scratch and a pinned result buffer, so
-the host->device copy of batch i+1 overlaps the kernels of batch i and the device->host copy of batch i-1.
+the host->device copy of batch i+1 overlaps the kernels of batch i and the device->host copy of batch i-1 (three slots keep
+the GPU fed while the host is blocked reading a result).
 """
 from __future__ import annotations
 
@@ -24,7 +25,7 @@ class _Slot:
 
 
 class HostExtractor:
-    def __init__(self, model, n_slots: int = 2):
+    def __init__(self, model, n_slots: int = 3):
         self.model = model
         self.device = model._device()
         if self.device.type != "cuda":
