@@ -100,10 +100,10 @@ def run_reference(args, rank, world):
     sample = 64  # utterances of the 256-utterance batch per step (bounded CPU sample)
     x = ox.synth_mfcc(sample, FRAMES, seed=1234)
     for _ in range(args.warmup):
-        ox.extract_x_vec_t(sd, x, 6)
+        ox.extract_x_vec_aten(sd, x, 6)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ox.extract_x_vec_t(sd, x, 6)
+        ox.extract_x_vec_aten(sd, x, 6)
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
     line = {"impl": "reference", "metric": "x-vectors/sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -112,7 +112,7 @@ def run_reference(args, rank, world):
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "frames": FRAMES,
                        "parallelism": "reference CPU implementation (oracle port), rank 0 only, all host threads"},
             "cpu_baseline": {"value": v, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{sample} of the {BATCH} utterances of a batch per step, oracle/xvector_oracle.extract_x_vec_t (fp32 torch CPU)"},
+                             "sample": f"{sample} of the {BATCH} utterances of a batch per step, oracle/xvector_oracle.extract_x_vec_aten (the reference's ATen op sequence, fp32 torch CPU)"},
             "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -126,17 +126,17 @@ def cpu_baseline_leg(budget_s=12.0):
     sd = ox.make_state_dict(seed=0)
     x = ox.synth_mfcc(64, FRAMES, seed=1234)  # BASELINE.json configs[0]
     for _ in range(2):
-        ox.extract_x_vec_t(sd, x, 6)
+        ox.extract_x_vec_aten(sd, x, 6)
     times = []
     t_end = time.perf_counter() + budget_s
     while len(times) < 5 or (time.perf_counter() < t_end and len(times) < 50):
         t0 = time.perf_counter()
-        ox.extract_x_vec_t(sd, x, 6)
+        ox.extract_x_vec_aten(sd, x, 6)
         times.append(time.perf_counter() - t0)
     times.sort()
     med = times[len(times) // 2]
     return {"value": 64 / med, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"config c1 (64 x 300 x 24, batch 64), median of {len(times)} runs of the oracle port (fp32 torch CPU ops of the reference path)",
+            "sample": f"config c1 (64 x 300 x 24, batch 64), median of {len(times)} runs of oracle.extract_x_vec_aten (the reference's ATen op sequence, fp32 torch CPU)",
             "frames_per_sec": 64 * FRAMES / med, "gflops": 64 * flops_per_utt(FRAMES) / med / 1e9, "best_utt_s": 64 / times[0]}
 
 

@@ -243,6 +243,30 @@ def extract_x_vec_np(sd, x: np.ndarray, x_vec_extract_layer: int = 6) -> np.ndar
 
 
 @torch.no_grad()
+def extract_x_vec_aten(sd, x: torch.Tensor, x_vec_extract_layer: int = 6) -> torch.Tensor:
+    """Same result as extract_x_vec_t, but issuing the ATen operator sequence the reference issues on this path — k shifted
+    views + cat (tdnn_layer.py:28-29), addmm (:30), clamp_min (:31), native_batch_norm in eval mode on the transposed view
+    (:36-39), mean + std + cat (main.py:60-62), addmm (main.py:87-90) — so that its wall time is the reference's CPU time.
+    This is what bench.py times as the CPU baseline / `--impl reference` arm."""
+    import torch.nn.functional as F
+    h = x
+    for i, ctx in enumerate(LAYER_CONTEXTS):
+        span, t_in = ctx[-1] - ctx[0], h.shape[1]
+        views = [h[:, c - ctx[0]: t_in - span + (c - ctx[0]), :] for c in ctx]
+        h = F.relu(F.linear(torch.cat(views, 2), _as_t(sd[f"time_context_layers.{i}.linear.weight"]),
+                            _as_t(sd[f"time_context_layers.{i}.linear.bias"])))
+        bn = _bn_of(sd, i, _as_t)
+        if bn is not None:
+            gamma, beta, mean, var = bn
+            h = F.batch_norm(h.transpose(1, 2), mean, var, gamma, beta, False, 0.1, BN_EPS).transpose(1, 2)
+    pooled = torch.cat((torch.mean(h, 1), torch.std(h, 1)), 1)
+    s6 = F.linear(pooled, _as_t(sd["segment_layer6.weight"]), _as_t(sd["segment_layer6.bias"]))
+    if x_vec_extract_layer == 7:
+        return F.linear(F.relu(s6), _as_t(sd["segment_layer7.weight"]), _as_t(sd["segment_layer7.bias"]))
+    return s6
+
+
+@torch.no_grad()
 def forward_t(sd, x: torch.Tensor) -> torch.Tensor:
     """main.py:66-75 — classifier logits (B,num_classes): relu(seg6) -> relu(seg7) -> output."""
     p = stat_pool_t(tdnn_stack_t(sd, x))

@@ -60,6 +60,14 @@ def test_extract_matches_golden(golden, state_dict, tag):
     assert rel_err(ox.extract_x_vec_np(state_dict, x.numpy(), 6), golden[tag + "_l6"]) < 2e-5
 
 
+def test_aten_sequence_port_matches_golden(golden, state_dict):
+    """The operator-sequence port that bench.py times as the CPU baseline gives the reference's numbers."""
+    b, t, seed = golden["b8_t300_shape_seed"].tolist()
+    x = ox.synth_mfcc(b, t, seed=seed)
+    for layer, key in ((6, "_l6"), (7, "_l7")):
+        assert rel_err(ox.extract_x_vec_aten(state_dict, x, layer).numpy(), golden["b8_t300" + key]) < 2e-6
+
+
 def test_single_pooled_frame_is_nan_like_reference(golden, state_dict):
     b, t, seed = golden["b2_t15_shape_seed"].tolist()
     got = ox.extract_x_vec_t(state_dict, ox.synth_mfcc(b, t, seed=seed), 6).numpy()
