@@ -138,6 +138,25 @@ XVEC_API int xvec_pool_finalize(const float* part_dev, const int32_t* slot_start
                        int p, const float* bn_scale_dev, const float* bn_shift_dev, float* out_f32_dev,
                        void* out_lp_dev, int out_lp_dtype, int64_t out_lp_ld, void* stream);
 
+/* MFCC front end (the step BEFORE the path): waveform -> (frames, 24) float32 rows of the flat frame
+ * matrix, with the reference's fixed parameters: 16 kHz, pre-emphasis 0.97, 400-sample frames every 160 samples (zero padded,
+ * rectangular window), 512-point power spectrum / 512, 26 triangular mel filters on integer bins, log, orthonormal DCT-II
+ * (first 24), lifter 22, coefficient 0 = log frame energy.
+ * replaces: python_speech_features.mfcc(sample, 16000, numcep=24, nfilt=26, nfft=512) (dataset.py:130); that package is not
+ * available offline, so parity for this entry point is UNPINNED (checked against oracle/mfcc_oracle.py only).
+ *   wav_dev        float32 or int16 samples of all utterances; utterance u = wav[wav_start[u] .. + wav_len[u])
+ *   row_start_dev  int64 first output row of utterance u; n_frames_dev int32 = xvec_mfcc_num_frames(wav_len[u])
+ *   norm_offset_dev / norm_scale_dev  optional per-utterance affine applied to the samples first, x' = (x + offset) * scale
+ *                  (from xvec_wav_minmax = the reference's min-max normalisation, dataset.py:217-218), or both NULL
+ *   out_dev        (total_frames, >= 24) float32 with row stride out_ld */
+XVEC_API int64_t xvec_mfcc_num_frames(int64_t n_samples);
+XVEC_API int xvec_mfcc(const void* wav_dev, int wav_is_int16, const int64_t* wav_start_dev, const int32_t* wav_len_dev,
+              const int64_t* row_start_dev, const int32_t* n_frames_dev, int n_utts, int max_frames,
+              const float* norm_offset_dev, const float* norm_scale_dev, float* out_dev, int64_t out_ld, void* stream);
+/* Per-utterance (offset, scale) = (-min, 1/(max-min)) of the raw samples: x -= min(x); x /= max(x) (dataset.py:217-218). */
+XVEC_API int xvec_wav_minmax(const void* wav_dev, int wav_is_int16, const int64_t* wav_start_dev, const int32_t* wav_len_dev,
+                    int n_utts, float* norm_offset_dev, float* norm_scale_dev, void* stream);
+
 /* float32 -> dtype copy of a (rows, cols) matrix (row strides in elements); XVEC_F32 is a strided copy.
  * replaces: samples.float() (main.py:137) for the bf16 pipeline. */
 XVEC_API int xvec_cast(const float* src_dev, int64_t src_ld, void* dst_dev, int dst_dtype, int64_t dst_ld, int64_t rows,

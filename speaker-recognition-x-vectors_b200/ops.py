@@ -172,6 +172,43 @@ def stats_pool_ragged(x: torch.Tensor, row_start: np.ndarray, n_rows: np.ndarray
     return pool_finalize(part, ss_d, nr_d, p, out_lp=out_lp)
 
 
+def mfcc(wav: torch.Tensor, wav_lengths, normalize: bool = True, out: torch.Tensor | None = None):
+    """Waveforms -> flat MFCC frame matrix on the GPU.  `wav` is a 1-D CUDA tensor (float32 or int16) holding all utterances
+    back to back, `wav_lengths` their sample counts.  normalize=True applies the reference's per-utterance min-max
+    normalisation first.  Returns (flat (sum frames, 24) float32, frame counts int64 numpy) — exactly what
+    XVectorModel.extract_x_vec_flat takes."""
+    _require_cuda(wav, out)
+    lib = _lib.load()
+    if wav.dim() != 1 or wav.dtype not in (torch.float32, torch.int16) or not wav.is_contiguous():
+        raise ValueError("wav must be a contiguous 1-D float32 or int16 tensor")
+    wl = np.asarray(wav_lengths, dtype=np.int64).reshape(-1)
+    if wl.size == 0 or (wl <= 0).any() or int(wl.sum()) != wav.numel() or wl.max() >= 2**31:
+        raise ValueError("wav_lengths must be positive and sum to wav.numel()")
+    if wl.size > 65535:
+        raise ValueError("at most 65535 utterances per call")
+    nf = np.asarray([lib.xvec_mfcc_num_frames(int(v)) for v in wl], dtype=np.int64)
+    wstart = np.concatenate(([0], np.cumsum(wl)[:-1]))
+    rstart = np.concatenate(([0], np.cumsum(nf)[:-1]))
+    dev = wav.device
+    meta64 = torch.from_numpy(np.stack([wstart, rstart])).to(dev)
+    meta32 = torch.from_numpy(np.stack([wl, nf]).astype(np.int32)).to(dev)
+    total = int(nf.sum())
+    if out is None:
+        out = torch.empty((total, 24), dtype=torch.float32, device=dev)
+    if out.dim() != 2 or out.shape[0] != total or out.shape[1] < 24 or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError("out must be float32 (sum frames, >=24) with unit column stride")
+    is16 = int(wav.dtype == torch.int16)
+    with torch.cuda.device(dev):
+        off = scl = None
+        if normalize:
+            off = torch.empty(wl.size, dtype=torch.float32, device=dev)
+            scl = torch.empty(wl.size, dtype=torch.float32, device=dev)
+            check(lib.xvec_wav_minmax(ptr(wav), is16, ptr(meta64[0]), ptr(meta32[0]), wl.size, ptr(off), ptr(scl), stream_ptr()))
+        check(lib.xvec_mfcc(ptr(wav), is16, ptr(meta64[0]), ptr(meta32[0]), ptr(meta64[1]), ptr(meta32[1]), wl.size, int(nf.max()),
+                            ptr(off), ptr(scl), ptr(out), out.stride(0), stream_ptr()))
+    return out, nf
+
+
 def cast(src: torch.Tensor, dtype: torch.dtype, out: torch.Tensor | None = None) -> torch.Tensor:
     _require_cuda(src, out)
     lib = _lib.load()
