@@ -265,6 +265,16 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t tbase = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
       const int row0 = m0 + q * 32;
       const int row = row0 + lane;
+      // The accumulator buffer goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld of the tile has landed in
+      // registers — the math / staging / stores of that last chunk then overlap the MMAs of tile i+2.
+      bool released = false;
+      auto release_tmem = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+        released = true;
+      };
+      const int c_last = min(cend, p.n - n0) - 1;  // last valid column of this warp's range (may be < cbeg)
 
       if constexpr (kEpi == EPI_POOL) {
         // per warp: 32 rows x 32 columns at a time, transposed through smem so that lane == column; column sums of
@@ -278,6 +288,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[32];
           tmem_ld_32x32(tbase + c, v);
           tmem_ld_wait();
+          if (c + 32 > c_last) release_tmem();
 #pragma unroll
           for (int j = 0; j < 32; ++j)  // tr[column j][row lane], row group (lane/4) stored at slot (lane/4 ^ j%8)
             tr[j * 32 + ((((lane >> 2) ^ (j & 7)) << 2) | (lane & 3))] = __uint_as_float(v[j]);
@@ -352,6 +363,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (warp == 2 && lane == 0 && c == cbeg && cc == 0) trace(p, it, 8);
               tmem_ld_32x32(tbase + c + cc * 32, v);
               tmem_ld_wait();
+              if (c + cc * 32 + 32 > c_last) release_tmem();
               if (warp == 2 && lane == 0 && c == cbeg && cc == 0) trace(p, it, 9);
             } else {
 #pragma unroll
@@ -448,12 +460,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      // all of this warp's TMEM reads of the buffer are complete -> hand it back to the leader's MMA issuer
-      if (warp == 2 && lane == 0) trace(p, it, 12);
-      tc_fence_before();
-      __syncwarp();
-      if (warp == 2 && lane == 0) trace(p, it, 13);
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+      if (!released) release_tmem();  // nothing was read (no pooled rows / no valid columns in this warp's range)
       if (warp == 2 && lane == 0) trace(p, it, 7);
     }
     if constexpr (kEpi != EPI_POOL) {
