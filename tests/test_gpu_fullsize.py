@@ -116,3 +116,22 @@ def test_c5_voxceleb_sized_sharded_and_trials(xb, state_dict):
         s = xb.ops.cosine_trials(torch.from_numpy(outs[precision]).float().cuda(), en, te, center=True).cpu().numpy()
         assert np.abs(s - s64).max() < margin, (precision, np.abs(s - s64).max(), margin)
         assert np.array_equal(s >= thr, s64 >= thr)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_edge_shapes_many_tiny_and_one_huge_utterance(xb, state_dict, precision):
+    """Edge cases of the flat layout: thousands of minimum-length utterances (several utterances per 32-row pooling
+    block, 15-frame utterances pool a single frame -> NaN std like torch.std) and one 10-minute utterance."""
+    m = _model(xb, state_dict, precision)
+    lens = np.concatenate([np.full(1500, 16), np.full(700, 15), ox.synth_lengths(800, 16, 40, seed=11)])
+    rng = np.random.default_rng(12)
+    rng.shuffle(lens)
+    utts = ox.synth_ragged(lens, seed=13)
+    out = m.extract_x_vec_flat(torch.cat(utts).cuda(), lens).cpu().numpy()
+    one_frame = lens == 15
+    assert np.isnan(out[one_frame]).all() and np.isfinite(out[~one_frame]).all()
+    sel = np.nonzero(~one_frame)[0][:: 97]
+    _parity(out[sel], ox.extract_ragged_t(state_dict, [utts[i] for i in sel], 6).numpy(), precision)
+    huge = ox.synth_mfcc(1, 60_000, seed=14)
+    got = m.extract_x_vec(huge.cuda()).cpu().numpy()
+    _parity(got, ox.extract_x_vec_t(state_dict, huge, 6).numpy(), precision)
