@@ -138,6 +138,36 @@ XVEC_API int xvec_pool_finalize(const float* part_dev, const int32_t* slot_start
                        int p, const float* bn_scale_dev, const float* bn_shift_dev, float* out_f32_dev,
                        void* out_lp_dev, int out_lp_dtype, int64_t out_lp_ld, void* stream);
 
+/* One layer of xvec_extract_forward: a TDNN layer (taps >= 1) or a fully connected layer (taps == 1), operands already
+ * packed with xvec_pack_weight in `dtype`; bias as for xvec_tdnn_layer (ceil(n/32)*32 floats) or NULL. */
+typedef struct XvecLayerDesc {
+  const void* w_packed_dev;
+  const float* bias_dev;
+  int32_t n;      /* output channels */
+  int32_t cin;    /* input channels per tap */
+  int32_t taps;
+  int32_t dtype;  /* XVEC_F32 / XVEC_BF16: element type of this layer's INPUT activations and packed weights */
+  int32_t tap_offsets[XVEC_MAX_TAPS];
+} XvecLayerDesc;
+
+/* The whole extraction path for one flat batch in ONE call (8 kernel launches enqueued on `stream`, no host work besides
+ * the tensor-map encodes): TDNN layers 0..n_tdnn-2 with ReLU (xvec_tdnn_layer), the last TDNN layer fused with pooling
+ * (xvec_tdnn_pool_fused), xvec_pool_finalize, then the n_fc segment layers (ReLU between them, none after the last).
+ * replaces: XVectorModel.extract_x_vec (main.py:81-94) = time_context_layers (main.py:38-44) + stat_pool (:59-63) +
+ * segment_layer6 [+ relu + segment_layer7]; eval-mode BatchNorm of layers 0..n-2 must already be folded into the next
+ * layer's packed weights, the last TDNN layer's BatchNorm is passed as bn_last_scale/shift (or NULL).
+ *   x_dev (rows, tdnn[0].cin) float32, row stride x_ld;  act0/act1: ping-pong activation buffers (rows, act_ld) of the
+ *   dtype of tdnn[1];  layout arrays as for xvec_tdnn_pool_fused / xvec_pool_finalize;  part_dev (n_slots, 2, n_last);
+ *   pooled_dev float32 (n_utts, 2 n_last);  pooled_lp_dev same in fc[0].dtype when that is XVEC_BF16, else NULL;
+ *   fc_tmp_dev (n_utts, fc[0].n) of fc[1].dtype when n_fc == 2;  out_dev float32 (n_utts, fc[n_fc-1].n), row stride out_ld;
+ *   splitk_ws_dev: scratch for the segment layers (see xvec_splitk_workspace_bytes) or NULL. */
+XVEC_API int xvec_extract_forward(const XvecLayerDesc* tdnn_host, int n_tdnn, const float* x_dev, int64_t rows, int64_t x_ld,
+                         void* act0_dev, void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev,
+                         const int32_t* blk_slot_base_dev, const int32_t* utt_slot_start_dev, const int32_t* n_pool_dev,
+                         int n_utts, float* part_dev, const float* bn_last_scale_dev, const float* bn_last_shift_dev,
+                         float* pooled_dev, void* pooled_lp_dev, const XvecLayerDesc* fc_host, int n_fc, void* fc_tmp_dev,
+                         void* splitk_ws_dev, int64_t splitk_ws_bytes, float* out_dev, int64_t out_ld, void* stream);
+
 /* MFCC front end (the step BEFORE the path): waveform -> (frames, 24) float32 rows of the flat frame
  * matrix, with the reference's fixed parameters: 16 kHz, pre-emphasis 0.97, 400-sample frames every 160 samples (zero padded,
  * rectangular window), 512-point power spectrum / 512, 26 triangular mel filters on integer bins, log, orthonormal DCT-II

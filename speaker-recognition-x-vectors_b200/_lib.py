@@ -18,6 +18,12 @@ E_ARG, E_CUDA, E_DEVICE = -1, -2, -3
 TILE_N, POOL_BLOCK, POOL_CHUNK, MAX_TAPS = 256, 32, 128, 8
 ABI_VERSION = 2
 
+class LayerDesc(ctypes.Structure):
+    """XvecLayerDesc of include/xvec_b200.h."""
+    _fields_ = [("w_packed_dev", c_void_p), ("bias_dev", c_void_p), ("n", c_int32), ("cin", c_int32), ("taps", c_int32),
+                ("dtype", c_int32), ("tap_offsets", c_int32 * MAX_TAPS)]
+
+
 _SIGNATURES = {
     "xvec_abi_version": (c_int, []),
     "xvec_last_error": (c_char_p, []),
@@ -37,6 +43,9 @@ _SIGNATURES = {
                                         c_void_p, c_void_p]),
     "xvec_pool_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int64, c_void_p]),
+    "xvec_extract_forward": (c_int, [POINTER(LayerDesc), c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LayerDesc), c_int,
+                                     c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "xvec_mfcc_num_frames": (c_int64, [c_int64]),
     "xvec_mfcc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "xvec_wav_minmax": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

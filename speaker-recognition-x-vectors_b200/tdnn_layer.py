@@ -47,7 +47,9 @@ class TdnnLayer(nn.Module):
         ts = [self.linear.weight, self.linear.bias]
         if self.batch_norm:
             ts += [self.norm.weight, self.norm.bias, self.norm.running_mean, self.norm.running_var]
-        return tuple((t.data_ptr(), t._version, str(t.device)) for t in ts if t is not None)
+        # (identity, in-place version) per parameter: cheap enough for the per-batch hot path; .to()/.cuda() create new
+        # tensors (new identity), load_state_dict / optimiser steps bump the version
+        return tuple((id(t), t._version) for t in ts if t is not None)
 
     def prepared(self, dtype: torch.dtype, fold_bn: bool = True):
         """(w_packed, bias, bn_scale, bn_shift) on the parameters' device; re-packed when parameters change."""

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .layout import utterance_layout
 from .tdnn_layer import TdnnLayer, _aligned_rows, tap_offsets
 
@@ -79,6 +79,8 @@ class _Scratch:
         self.ld = (max(widths) + per16 - 1) // per16 * per16
         self.rows_cap = self.slots_cap = self.utts_cap = 0
         self.act = self.part = self.pooled = self.pooled_lp = None
+        self.fc_tmp = self.ws = None
+        self.ws_for = None
 
     def ensure(self, rows, n_slots, n_utts):
         if rows > self.rows_cap:
@@ -92,6 +94,19 @@ class _Scratch:
             self.pooled = torch.empty((self.utts_cap, 2 * self.pool_dim), dtype=torch.float32, device=self.device)
             self.pooled_lp = (torch.empty((self.utts_cap, 2 * self.pool_dim), dtype=self.act_dtype, device=self.device)
                               if self.act_dtype != torch.float32 else None)
+            self.fc_tmp = None
+
+    def ensure_head(self, n_utts, fc_shapes, width):
+        """Scratch of the segment layers: the hidden (n_utts, width) activation and the split-K workspace."""
+        if self.fc_tmp is None or self.fc_tmp.shape[0] < n_utts or self.fc_tmp.shape[1] != width:
+            self.fc_tmp = torch.empty((max(n_utts, self.utts_cap), width), dtype=self.act_dtype, device=self.device)
+        key = (n_utts, tuple(fc_shapes))
+        if self.ws_for != key:
+            lib = _lib.load()
+            need = max(lib.xvec_splitk_workspace_bytes(n_utts, cin, 1, n, _lib.dtype_code(self.act_dtype)) for cin, n in fc_shapes)
+            if need > 0 and (self.ws is None or self.ws.numel() < need):
+                self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self.ws_for = key
 
 
 class XVectorModel(nn.Module):
@@ -193,9 +208,42 @@ class XVectorModel(nn.Module):
         self._fc_prep["stack"] = (fp, res)
         return res
 
+    def _pipeline(self):
+        """XvecLayerDesc arrays for xvec_extract_forward (one C call per batch), rebuilt when parameters change."""
+        layers = list(self.time_context_layers)
+        use7 = self.x_vec_extract_layer == 7
+        fcs = [self.segment_layer6, self.segment_layer7] if use7 else [self.segment_layer6]
+        fp = (tuple(l._fingerprint() for l in layers), self.precision, use7,
+              tuple((id(f.weight), f.weight._version, id(f.bias), f.bias._version if f.bias is not None else -1) for f in fcs))
+        hit = self._fc_prep.get("pipeline")
+        if hit is not None and hit[0] == fp:
+            return hit[1]
+        stack, (scale5, shift5) = self._stack_params()
+        code = _lib.dtype_code
+        tdnn = (_lib.LayerDesc * len(layers))()
+        for i, (layer, (w, bias, offs)) in enumerate(zip(layers, stack)):
+            d = tdnn[i]
+            d.w_packed_dev, d.bias_dev = w.data_ptr(), (bias.data_ptr() if bias is not None else None)
+            d.n, d.cin, d.taps, d.dtype = layer.output_size, layer.input_size, len(offs), code(w.dtype)
+            for j, o in enumerate(offs):
+                d.tap_offsets[j] = o
+        fc = (_lib.LayerDesc * len(fcs))()
+        keep = []
+        for i, lin in enumerate(fcs):
+            w, b = self._fc(lin, self.act_dtype)
+            keep.append((w, b))
+            d = fc[i]
+            d.w_packed_dev, d.bias_dev = w.data_ptr(), (b.data_ptr() if b is not None else None)
+            d.n, d.cin, d.taps, d.dtype = lin.out_features, lin.in_features, 1, code(w.dtype)
+            d.tap_offsets[0] = 0
+        res = {"tdnn": tdnn, "n_tdnn": len(layers), "fc": fc, "n_fc": len(fcs), "keep": (stack, keep, scale5, shift5),
+               "scale5": scale5, "shift5": shift5, "out_dim": fcs[-1].out_features, "hidden": fcs[0].out_features,
+               "fc_shapes": [(f.in_features, f.out_features) for f in fcs]}
+        self._fc_prep["pipeline"] = (fp, res)
+        return res
+
     def _fc(self, lin: nn.Linear, dtype):
-        fp = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr() if lin.bias is not None else 0,
-              lin.bias._version if lin.bias is not None else 0, str(lin.weight.device))
+        fp = (id(lin.weight), lin.weight._version, id(lin.bias), lin.bias._version if lin.bias is not None else 0)
         hit = self._fc_prep.get((id(lin), dtype))
         if hit is not None and hit[0] == fp:
             return hit[1]
@@ -255,9 +303,33 @@ class XVectorModel(nn.Module):
 
     def extract_x_vec_flat(self, flat_x: torch.Tensor, lengths, slot: int = 0) -> torch.Tensor:
         """Ragged extraction: flat (sum(lengths), input_size) frames -> float32 (len(lengths), x_vector_size).
-        `slot` selects an independent scratch set so that calls on different CUDA streams can overlap."""
-        pooled, pooled_lp = self.pooled_stats_flat(flat_x, lengths, slot)
-        return self._head(pooled, pooled_lp, self.x_vec_extract_layer)
+        `slot` selects an independent scratch set so that calls on different CUDA streams can overlap.
+        The whole path is ONE C-ABI call (xvec_extract_forward) that enqueues its 8 kernels on the current stream."""
+        self._check_eval()
+        if not flat_x.is_cuda:
+            raise ValueError("xvec_b200 has no CPU path: move the input (and the model) to a CUDA device")
+        if flat_x.dim() != 2 or flat_x.shape[1] != self.input_size:
+            raise ValueError(f"expected a flat (rows, {self.input_size}) frame matrix")
+        lay = self._layout_for(lengths)
+        if lay.rows != flat_x.shape[0]:
+            raise ValueError("sum(lengths) does not match the number of rows")
+        pipe = self._pipeline()
+        sc = self._scratch_for(slot)
+        sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
+        sc.ensure_head(lay.n_utts, pipe["fc_shapes"], pipe["hidden"])
+        if flat_x.dtype != torch.float32:
+            flat_x = flat_x.float()
+        x = _aligned_rows(flat_x)
+        out = torch.empty((lay.n_utts, pipe["out_dim"]), dtype=torch.float32, device=flat_x.device)
+        lib = _lib.load()
+        p = _lib.ptr
+        with torch.cuda.device(flat_x.device):
+            _lib.check(lib.xvec_extract_forward(
+                pipe["tdnn"], pipe["n_tdnn"], p(x), lay.rows, x.stride(0), p(sc.act[0]), p(sc.act[1]), sc.ld, p(lay.row_utt),
+                p(lay.blk_slot_base), p(lay.utt_slot_start), p(lay.n_pool), lay.n_utts, p(sc.part), p(pipe["scale5"]), p(pipe["shift5"]),
+                p(sc.pooled), p(sc.pooled_lp), pipe["fc"], pipe["n_fc"], p(sc.fc_tmp), p(sc.ws),
+                0 if sc.ws is None else sc.ws.numel(), p(out), out.stride(0), _lib.stream_ptr()))
+        return out
 
     # ------------------------------------------------------------------ reference surface
     def extract_x_vec(self, x: torch.Tensor) -> torch.Tensor:
