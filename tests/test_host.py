@@ -146,3 +146,17 @@ def test_state_dict_interchange_with_live_reference():
     res = ours.load_state_dict({k: v for k, v in ref.state_dict().items() if k in own}, strict=True)
     assert not res.missing_keys
     assert torch.equal(ours.segment_layer6.weight, ref.segment_layer6.weight)
+
+
+def test_load_reference_checkpoint_roundtrip(tmp_path):
+    """A Lightning checkpoint as the reference writes it (main.py:198,213): torch.save dict with 'state_dict' (+ extras)."""
+    sd = ox.make_state_dict(seed=0)
+    extra = dict(sd)
+    extra["accuracy.tp"] = torch.zeros(1)          # torchmetrics state that the reference's module also saves
+    path = str(tmp_path / "last.ckpt")
+    torch.save({"state_dict": extra, "hyper_parameters": {"x_vec_extract_layer": 6}, "epoch": 3}, path)
+    m = xvec_b200.XVectorModel()
+    res = m.load_reference_checkpoint(path)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in sd.items():
+        assert torch.equal(m.state_dict()[k], v), k
