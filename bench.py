@@ -9,7 +9,7 @@ A step = one pass of the hot path (TDNN1-5 -> statistics pooling -> segment6) ov
   value      utterances/s, device-resident inputs (more distinct batches than fit in L2), K steps in one CUDA-event bracket,
              two batches in flight on two streams
   e2e        utterances/s through the public host API (HostExtractor): pinned host MFCCs -> H2D -> kernels -> D2H x-vectors
-  roofline   tcgen05 TDNN kernel: algorithmic FLOPs of its launches / their CUDA-event time vs MEASURED_PEAKS.json
+  roofline   tcgen05 TDNN stack kernel: algorithmic FLOPs of a launch / its CUDA-event time vs MEASURED_PEAKS.json
   cpu_baseline  the oracle (port of the reference's fp32 PyTorch path) on this box's host cores, bounded sample
 Prints ONE JSON line on rank 0.
 """
@@ -222,6 +222,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- per-kernel timing of the dominant kernel (separate instrumented pass; not part of the numbers above)
     layer_ms = instrumented_layer_times(model, x_dev, lengths, n_res, iters=max(5, min(args.steps, 20)))
+    stack_ms = instrumented_stack_time(model, x_dev, lengths, n_res, iters=max(10, min(args.steps, 50)))
 
     dev_ms_t = torch.tensor([dev_ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -233,9 +234,8 @@ def run_b200(args, rank, world, local_rank):
         utts = BATCH * args.steps * world
         value = utts / (dev_ms / 1e3)
         e2e = utts / (e2e_ms / 1e3)
-        tdnn_ms = sum(layer_ms[f"tdnn{i + 1}"] for i in range(5))
         tdnn_flops = BATCH * sum(f * (FRAMES - l) for f, l in zip(FLOPS_L, LOST))
-        achieved = tdnn_flops / (tdnn_ms / 1e3) / 1e12
+        achieved = tdnn_flops / (stack_ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"] if precision == "bf16" else peaks["bf16_tflops_sustained"] / 2
         per_layer = {k: {"ms": round(v, 5)} for k, v in layer_ms.items()}
         for i in range(5):
@@ -254,16 +254,17 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": hx.h2d_bytes // args.steps, "d2h_bytes_per_step": hx.d2h_bytes // args.steps,
                     "api": "HostExtractor.submit/result (pinned host MFCCs in, pinned host x-vectors out, 3 slots / streams)",
                     "frames_per_sec": e2e * FRAMES, "checksum": checksum},
-            "gpu_launches": args.steps * 8,
+            "gpu_launches": args.steps * 4,  # tdnn_stack_kernel, pool_finalize_kernel, tdnn_gemm_kernel (segment6, split-K), splitk_reduce_kernel
             "clocks": clocks,
             "wall_ms_per_step": t_wall / args.steps * 1e3,
-            "roofline": {"kernel": "tdnn_gemm_kernel (5 launches/step: TDNN1-4 store epilogue, TDNN5 fused pooling epilogue)",
+            "roofline": {"kernel": "tdnn_stack_kernel (1 launch/step: all tiles of TDNN1-5 from one work queue; TDNN5 epilogue = pooling partials)",
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 100463616 if precision == "bf16" else None,  # dram bytes read+write of one TDNN2 launch (ncu, profiles/r01_v5_ncu_full_summary.txt)
+                         "traffic": STACK_DRAM_BYTES.get(precision),
                          "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops_sustained" + ("" if precision == "bf16" else " / 2 (TF32)"),
                          "frac_of_burst_peak": achieved / (peaks["bf16_tflops"] if precision == "bf16" else peaks["bf16_tflops"] / 2),
-                         "algorithmic_flops_per_step": tdnn_flops, "ms_per_step": tdnn_ms},
-            "kernels": per_layer,
+                         "algorithmic_flops_per_launch": tdnn_flops, "ms_per_launch": stack_ms,
+                         "timing": "CUDA events around each launch on its stream, launches back to back on one stream, averaged"},
+            "per_layer_launches": per_layer,  # the same layers as one tdnn_gemm_kernel launch each (XVEC_STACK=0 path), for comparison
         }
         if world == 1:
             line["roofline_pool"] = pooling_roofline(model, dev, peaks)
@@ -273,6 +274,32 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE tdnn_stack_kernel launch on this workload (ncu --set full, profiles/)
+STACK_DRAM_BYTES = {}
+
+
+def instrumented_stack_time(model, x_dev, lengths, n_batches, iters):
+    """Average CUDA-event duration of the tdnn_stack_kernel launch (incl. the 5 KB control-block memset it is enqueued with)."""
+    import torch
+    from xvec_b200 import ops
+    from xvec_b200.tdnn_layer import _aligned_rows
+    lay = model._layout_for(lengths)
+    sc = model._scratch_for(0)
+    sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
+    pipe = model._pipeline()
+    part = sc.part[: lay.n_slots]
+    evs = []
+    for it in range(iters + 3):
+        x = _aligned_rows(x_dev[it % n_batches])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], x, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs[3:]) / iters
 
 
 def instrumented_layer_times(model, x_dev, lengths, n_batches, iters):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XVEC_ABI_VERSION 2
+#define XVEC_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define XVEC_API __attribute__((visibility("default")))
@@ -47,6 +47,8 @@ extern "C" {
 #define XVEC_TILE_N 256     /* output-channel tile; packed weights are padded to a multiple of this many rows */
 #define XVEC_POOL_BLOCK 32  /* rows per pooling partial block of the fused TDNN5+pool epilogue */
 #define XVEC_POOL_CHUNK 128 /* rows per partial of the standalone statistics-pooling kernel */
+#define XVEC_MAX_STACK 6           /* TDNN layers xvec_tdnn_stack can chain in one launch */
+#define XVEC_STACK_MAX_BANDS 512   /* scheduling bands of xvec_tdnn_stack (internal table size) */
 
 XVEC_API int xvec_abi_version(void);
 XVEC_API const char* xvec_last_error(void);
@@ -150,9 +152,24 @@ typedef struct XvecLayerDesc {
   int32_t tap_offsets[XVEC_MAX_TAPS];
 } XvecLayerDesc;
 
-/* The whole extraction path for one flat batch in ONE call (8 kernel launches enqueued on `stream`, no host work besides
- * the tensor-map encodes): TDNN layers 0..n_tdnn-2 with ReLU (xvec_tdnn_layer), the last TDNN layer fused with pooling
- * (xvec_tdnn_pool_fused), xvec_pool_finalize, then the n_fc segment layers (ReLU between them, none after the last).
+/* The frame-level stack in ONE persistent kernel launch: TDNN layers 0..n_tdnn-2 (bias + ReLU, activations ping-ponged through
+ * act0/act1) and the last TDNN layer fused with the pooling partials (as xvec_tdnn_pool_fused).  Every (layer, 256-frame tile,
+ * 256-channel tile) is a work item drawn in order from a global counter by the CTA pairs; a tile of layer l+1 starts as soon as
+ * the tiles of layer l it reads are complete (per-tile flags in ctrl_dev), so the layers overlap inside the launch.
+ * replaces: time_context_layers (main.py:38-44) applied by extract_x_vec (main.py:82) + the reads of stat_pool (main.py:59-63).
+ *   tdnn_host[0].dtype must be XVEC_F32 (the MFCCs); layers 1.. share one dtype (the activation dtype); layers 0..n-2 need
+ *   n % XVEC_TILE_N == 0 and a bias; eval-mode BatchNorm folded forward as for xvec_extract_forward.
+ *   ctrl_dev: 128-byte aligned scratch of xvec_stack_ctrl_bytes(rows, n_tdnn) bytes, private to this call until it completes
+ *   (the call zeroes it on `stream`).  Returns XVEC_E_ARG for stacks outside these limits (use the per-layer calls). */
+XVEC_API int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn);
+XVEC_API int xvec_tdnn_stack(const struct XvecLayerDesc* tdnn_host, int n_tdnn, const float* x_dev, int64_t rows, int64_t x_ld,
+                    void* act0_dev, void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev,
+                    float* part_dev, void* ctrl_dev, int64_t ctrl_bytes, void* stream);
+
+/* The whole extraction path for one flat batch in ONE call (4 kernel launches enqueued on `stream`, no host work besides
+ * the tensor-map encodes): xvec_tdnn_stack, xvec_pool_finalize, then the n_fc segment layers (ReLU between them, none after
+ * the last).  Without ctrl_dev (NULL) or for a stack xvec_tdnn_stack does not take, the TDNN layers run as one launch each
+ * (xvec_tdnn_layer / xvec_tdnn_pool_fused) — same results.
  * replaces: XVectorModel.extract_x_vec (main.py:81-94) = time_context_layers (main.py:38-44) + stat_pool (:59-63) +
  * segment_layer6 [+ relu + segment_layer7]; eval-mode BatchNorm of layers 0..n-2 must already be folded into the next
  * layer's packed weights, the last TDNN layer's BatchNorm is passed as bn_last_scale/shift (or NULL).
@@ -160,13 +177,15 @@ typedef struct XvecLayerDesc {
  *   dtype of tdnn[1];  layout arrays as for xvec_tdnn_pool_fused / xvec_pool_finalize;  part_dev (n_slots, 2, n_last);
  *   pooled_dev float32 (n_utts, 2 n_last);  pooled_lp_dev same in fc[0].dtype when that is XVEC_BF16, else NULL;
  *   fc_tmp_dev (n_utts, fc[0].n) of fc[1].dtype when n_fc == 2;  out_dev float32 (n_utts, fc[n_fc-1].n), row stride out_ld;
- *   splitk_ws_dev: scratch for the segment layers (see xvec_splitk_workspace_bytes) or NULL. */
+ *   splitk_ws_dev: scratch for the segment layers (see xvec_splitk_workspace_bytes) or NULL;
+ *   ctrl_dev / ctrl_bytes: scratch of xvec_tdnn_stack or NULL / 0. */
 XVEC_API int xvec_extract_forward(const XvecLayerDesc* tdnn_host, int n_tdnn, const float* x_dev, int64_t rows, int64_t x_ld,
                          void* act0_dev, void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev,
                          const int32_t* blk_slot_base_dev, const int32_t* utt_slot_start_dev, const int32_t* n_pool_dev,
                          int n_utts, float* part_dev, const float* bn_last_scale_dev, const float* bn_last_shift_dev,
                          float* pooled_dev, void* pooled_lp_dev, const XvecLayerDesc* fc_host, int n_fc, void* fc_tmp_dev,
-                         void* splitk_ws_dev, int64_t splitk_ws_bytes, float* out_dev, int64_t out_ld, void* stream);
+                         void* splitk_ws_dev, int64_t splitk_ws_bytes, float* out_dev, int64_t out_ld, void* ctrl_dev,
+                         int64_t ctrl_bytes, void* stream);
 
 /* MFCC front end (the step BEFORE the path): waveform -> (frames, 24) float32 rows of the flat frame
  * matrix, with the reference's fixed parameters: 16 kHz, pre-emphasis 0.97, 400-sample frames every 160 samples (zero padded,

@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get("XVEC_LIB") or os.path.join(HERE, "libxvec_b200.so")  
 F32, BF16 = 0, 1
 E_ARG, E_CUDA, E_DEVICE = -1, -2, -3
 TILE_N, POOL_BLOCK, POOL_CHUNK, MAX_TAPS = 256, 32, 128, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
+MAX_STACK = 6
 
 class LayerDesc(ctypes.Structure):
     """XvecLayerDesc of include/xvec_b200.h."""
@@ -45,7 +46,10 @@ _SIGNATURES = {
                                    c_int, c_int64, c_void_p]),
     "xvec_extract_forward": (c_int, [POINTER(LayerDesc), c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LayerDesc), c_int,
-                                     c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+                                     c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "xvec_stack_ctrl_bytes": (c_int64, [c_int64, c_int]),
+    "xvec_tdnn_stack": (c_int, [POINTER(LayerDesc), c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int64, c_void_p]),
     "xvec_mfcc_num_frames": (c_int64, [c_int64]),
     "xvec_mfcc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "xvec_wav_minmax": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

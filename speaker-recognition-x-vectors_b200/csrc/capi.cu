@@ -1,6 +1,7 @@
 // extern "C" surface of libxvec_b200.so (declared in include/xvec_b200.h) + small host utilities.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "xvec_internal.h"
 
@@ -65,6 +66,16 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+// XVEC_STACK=0 makes xvec_extract_forward run one launch per layer (developer A/B switch; both are sm_100a paths).
+static bool use_stack_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("XVEC_STACK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace xvec
 
 using namespace xvec;
@@ -109,32 +120,48 @@ int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin
                        nullptr, XVEC_F32, 0, row_utt_dev, blk_slot_base_dev, part_dev, rows, true, nullptr, 0, stream);
 }
 
+int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn) { return stack_ctrl_bytes(rows, n_tdnn); }
+
+int xvec_tdnn_stack(const XvecLayerDesc* tdnn, int n_tdnn, const float* x_dev, int64_t rows, int64_t x_ld, void* act0_dev, void* act1_dev,
+                    int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev, float* part_dev, void* ctrl_dev,
+                    int64_t ctrl_bytes, void* stream) {
+  if (!tdnn) return set_error(XVEC_E_ARG, "tdnn_host is NULL");
+  return stack_dispatch(tdnn, n_tdnn, x_dev, rows, x_ld, act0_dev, act1_dev, act_ld, row_utt_dev, blk_slot_base_dev, part_dev, ctrl_dev,
+                        ctrl_bytes, stream);
+}
+
 int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const float* x_dev, int64_t rows, int64_t x_ld, void* act0_dev,
                          void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev,
                          const int32_t* utt_slot_start_dev, const int32_t* n_pool_dev, int n_utts, float* part_dev,
                          const float* bn_last_scale_dev, const float* bn_last_shift_dev, float* pooled_dev, void* pooled_lp_dev,
                          const XvecLayerDesc* fc, int n_fc, void* fc_tmp_dev, void* splitk_ws_dev, int64_t splitk_ws_bytes,
-                         float* out_dev, int64_t out_ld, void* stream) {
+                         float* out_dev, int64_t out_ld, void* ctrl_dev, int64_t ctrl_bytes, void* stream) {
   if (!tdnn || n_tdnn < 2 || !fc || n_fc < 1 || n_fc > 2) return set_error(XVEC_E_ARG, "need >= 2 TDNN layers and 1 or 2 segment layers");
   if (!x_dev || !act0_dev || !act1_dev || !pooled_dev || !out_dev) return set_error(XVEC_E_ARG, "null pointer argument");
   if (n_fc == 2 && !fc_tmp_dev) return set_error(XVEC_E_ARG, "fc_tmp_dev is NULL");
-  void* act[2] = {act0_dev, act1_dev};
-  const void* h = x_dev;
-  int64_t h_ld = x_ld;
-  int rc;
-  for (int i = 0; i + 1 < n_tdnn; ++i) {
-    const XvecLayerDesc& l = tdnn[i];
-    const int out_dtype = tdnn[i + 1].dtype;
-    rc = gemm_dispatch(h, l.dtype, rows, l.cin, h_ld, l.w_packed_dev, l.n, l.tap_offsets, l.taps, l.bias_dev, nullptr, nullptr, 1,
-                       act[i & 1], out_dtype, act_ld, nullptr, nullptr, nullptr, rows, false, nullptr, 0, stream);
-    if (rc) return rc;
-    h = act[i & 1];
-    h_ld = act_ld;
-  }
   const XvecLayerDesc& last = tdnn[n_tdnn - 1];
-  rc = gemm_dispatch(h, last.dtype, rows, last.cin, h_ld, last.w_packed_dev, last.n, last.tap_offsets, last.taps, last.bias_dev, nullptr,
-                     nullptr, 1, nullptr, XVEC_F32, 0, row_utt_dev, blk_slot_base_dev, part_dev, rows, true, nullptr, 0, stream);
-  if (rc) return rc;
+  int rc;
+  if (ctrl_dev && use_stack_kernel() && stack_supported(tdnn, n_tdnn, rows)) {
+    rc = stack_dispatch(tdnn, n_tdnn, x_dev, rows, x_ld, act0_dev, act1_dev, act_ld, row_utt_dev, blk_slot_base_dev, part_dev, ctrl_dev,
+                        ctrl_bytes, stream);
+    if (rc) return rc;
+  } else {
+    void* act[2] = {act0_dev, act1_dev};
+    const void* h = x_dev;
+    int64_t h_ld = x_ld;
+    for (int i = 0; i + 1 < n_tdnn; ++i) {
+      const XvecLayerDesc& l = tdnn[i];
+      const int out_dtype = tdnn[i + 1].dtype;
+      rc = gemm_dispatch(h, l.dtype, rows, l.cin, h_ld, l.w_packed_dev, l.n, l.tap_offsets, l.taps, l.bias_dev, nullptr, nullptr, 1,
+                         act[i & 1], out_dtype, act_ld, nullptr, nullptr, nullptr, rows, false, nullptr, 0, stream);
+      if (rc) return rc;
+      h = act[i & 1];
+      h_ld = act_ld;
+    }
+    rc = gemm_dispatch(h, last.dtype, rows, last.cin, h_ld, last.w_packed_dev, last.n, last.tap_offsets, last.taps, last.bias_dev, nullptr,
+                       nullptr, 1, nullptr, XVEC_F32, 0, row_utt_dev, blk_slot_base_dev, part_dev, rows, true, nullptr, 0, stream);
+    if (rc) return rc;
+  }
   const int fc_in_dtype = fc[0].dtype;
   if (fc_in_dtype == XVEC_BF16 && !pooled_lp_dev) return set_error(XVEC_E_ARG, "pooled_lp_dev is required for bf16 segment layers");
   rc = xvec_pool_finalize(part_dev, utt_slot_start_dev, n_pool_dev, n_utts, last.n, bn_last_scale_dev, bn_last_shift_dev, pooled_dev,

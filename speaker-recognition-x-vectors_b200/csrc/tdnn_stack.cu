@@ -1,0 +1,534 @@
+// The whole frame-level TDNN stack (time_context_layers, main.py:38-44) as ONE persistent dataflow kernel — sm_100a only.
+//
+// tdnn_gemm.cu runs one layer per launch; a step then pays five launch latencies / prologues / drain tails and five wave
+// quantisations (600 tiles on 74 CTA pairs = 8.1 waves).  Here every (layer, 256-frame m-tile, 256-channel n-tile) of the
+// stack is one WORK ITEM of a single launch:
+//
+//   * dynamic tile scheduler: the leader CTA of each pair draws the next item with one atomicAdd on a global counter
+//     (prefetched one tile ahead) and hands it to all warp roles of both CTAs through a small shared-memory ring
+//     (mbarrier full/empty, the peer's copy written with st.shared::cluster + release/acquire at cluster scope).  Items are
+//     drawn strictly in order and an item only depends on EARLIER items, so any number of resident CTAs makes progress —
+//     two of these kernels on two streams cannot deadlock each other.
+//   * item order: bands of `band` m-tiles; inside a band layer 1, 2, ... L, the m-range of layer l skewed down by l tiles
+//     (layer l+1 tile m reads layer l tiles m-1.. m+1, all in the same or an earlier band).  A band's activations
+//     (band*256 rows x 512 ch) stay in L2 between the layers; short-K / store-bound layers overlap with MMA-bound ones.
+//   * inter-layer dependencies: every epilogue warp adds 1 to ready[layer][m_tile] (red.release.gpu) once its TMA stores of
+//     that tile are COMPLETE (cp.async.bulk.wait_group, deferred so that it never blocks a busy warp); the TMA producer of a
+//     consuming tile spins (ld.acquire.gpu) until the three tiles it touches are complete, then fence.proxy.async.
+//     The two ping-pong activation buffers are safe: tile (l, m) overwrites rows whose readers (l-1, m-1) and (l-1, m) it
+//     has just waited for.
+//
+// The mainloop, TMEM double buffering and both epilogues are the ones of tdnn_gemm.cu (gemm_tile.cuh); layer 1 always runs
+// kind::tf32 on the float32 MFCCs, the other layers kind::f16 (bf16) or kind::tf32 (kAllTf32).
+#include "gemm_tile.cuh"
+#include <cuda_bf16.h>
+
+namespace xvec {
+
+constexpr int STACK_STAGES = 5;
+constexpr int SCHED_SLOTS = 8;            // work-item ring between the scheduler and the warp roles
+constexpr uint32_t ITEM_DONE = 0xFFFFFFFFu;
+constexpr int SCHED_CONSUMERS = 2 * EPI_WARPS + 2;  // per slot: leader MMA warp + peer producer + 8 epilogue warps of each CTA
+
+struct StackLayer {
+  int n, n_tiles, taps, cpt;  // K loop = taps * cpt chunks of 128 bytes
+  int tf32;                   // operand kind of this layer (1: float32 activations / TF32 math, 0: bf16)
+  int tap_off[XVEC_MAX_TAPS];
+  const float* bias;
+};
+
+struct StackMaps {
+  CUtensorMap a[XVEC_MAX_STACK], b[XVEC_MAX_STACK], y[XVEC_MAX_STACK];
+};
+
+struct StackParams {
+  int rows, m_tiles, n_layers;
+  int band, n_bands;          // m-tiles per band; band_first[b] = first work item of band b
+  unsigned total_items;
+  StackLayer L[XVEC_MAX_STACK];
+  unsigned* counter;          // next work item (zeroed before the launch)
+  unsigned* ready;            // [(n_layers-1)][m_tiles] completed epilogue-warp stores per tile (zeroed before the launch)
+  const int* row_utt;
+  const int* blk_slot_base;
+  float* part;
+  unsigned long long pol_a, pol_b, pol_y;
+  unsigned band_first[XVEC_STACK_MAX_BANDS + 1];
+};
+
+// item -> (layer [0,3) | n_tile [3,8) | m_tile [8,32)).  Same arithmetic as stack_plan() on the host.
+__host__ __device__ inline int band_layer_range(int band, int m_tiles, int b, int l, int* lo) {
+  int a = b * band - l, z = (b + 1) * band - l;
+  if (a < 0) a = 0;
+  if (z > m_tiles) z = m_tiles;
+  *lo = a;
+  return z > a ? z - a : 0;
+}
+__device__ __forceinline__ uint32_t decode_item(const StackParams& p, unsigned item, int& band_cursor) {
+  while (item >= p.band_first[band_cursor + 1]) ++band_cursor;
+  unsigned r = item - p.band_first[band_cursor];
+  for (int l = 0; l < p.n_layers; ++l) {
+    int lo;
+    const unsigned nt = p.L[l].n_tiles;
+    const unsigned cnt = band_layer_range(p.band, p.m_tiles, band_cursor, l, &lo) * nt;
+    if (r < cnt) return static_cast<uint32_t>(l) | ((r % nt) << 3) | ((lo + r / nt) << 8);
+    r -= cnt;
+  }
+  return ITEM_DONE;  // unreachable when the host table is consistent
+}
+
+// K loop of one tile on the MMA warp (leader CTA, warp-uniform; see tdnn_gemm.cu).
+template <bool kTf32>
+__device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* full_bar, uint64_t* empty_bar, uint32_t d, int kblocks, int& stage,
+                                         uint32_t& phase, uint32_t& rdy) {
+  constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
+  for (int kb = 0; kb < kblocks; ++kb) {
+    if (!(rdy & 1u)) mbar_wait(&full_bar[stage], phase, 3);
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(base + stage * STAGE_BYTES);
+    const uint64_t da = umma_desc_sw128(a_addr);
+    const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
+    int stage_n = stage + 1;
+    uint32_t phase_n = phase;
+    if (stage_n == STACK_STAGES) { stage_n = 0; phase_n ^= 1u; }
+    rdy = umma_step_pair<kTf32>(elect_one() ? 1u : 0u, d, da, db, idesc, kb > 0 ? 1u : 0u, STEP_COMMIT_A | STEP_PROBE_A,
+                                smem_u32(&empty_bar[stage]), 0u, smem_u32(&full_bar[stage_n]), phase_n, 0u, 0u);
+    stage = stage_n;
+    phase = phase_n;
+  }
+}
+
+constexpr int stack_smem_bytes() { return 1024 + STACK_STAGES * STAGE_BYTES + EPI_WARPS * OUT_BUFS * OUT_BUF_BYTES; }
+
+template <bool kAllTf32>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant__ StackParams p) {
+  constexpr int STAGES = STACK_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t sfull_bar[SCHED_SLOTS], sempty_bar[SCHED_SLOTS];
+  __shared__ uint32_t sched_item[SCHED_SLOTS];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte alignment
+  uint8_t* epi_smem = base + STAGES * STAGE_BYTES;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader of the pair
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < p.n_layers; ++l) {
+      tma_prefetch_desc(&maps.a[l]);
+      tma_prefetch_desc(&maps.b[l]);
+      if (l + 1 < p.n_layers) tma_prefetch_desc(&maps.y[l]);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx (bytes of both CTAs)
+      mbar_init(&empty_bar[s], 1);  // leader's multicast commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);               // leader's multicast commit
+      mbar_init(&tempty_bar[b], 2 * EPI_WARPS);  // one arrive per epilogue warp of both CTAs (on the leader's barrier)
+    }
+    for (int s = 0; s < SCHED_SLOTS; ++s) {
+      mbar_init(&sfull_bar[s], 1);                 // the scheduler's arrive (local in the leader, remote in the peer)
+      mbar_init(&sempty_bar[s], SCHED_CONSUMERS);  // every consumer of both CTAs, on the leader's barrier
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // Consumer side of the work-item ring: wait for entry `it`, read it, hand the slot back to the scheduler.
+  auto ring_read = [&](int it) -> uint32_t {
+    const int slot = it % SCHED_SLOTS;
+    const uint32_t sph = (it / SCHED_SLOTS) & 1u;
+    if (rank == 0) mbar_wait(&sfull_bar[slot], sph, 6);
+    else mbar_wait_cluster(&sfull_bar[slot], sph, 6);
+    const uint32_t item = *reinterpret_cast<volatile uint32_t*>(&sched_item[slot]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sempty_bar[slot]), 0));
+    return item;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ scheduler (leader) + TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0, rdy = 0;
+    int band_cursor = 0;
+    unsigned nxt = 0;  // lane 0 of the leader: the prefetched next item
+    uint32_t leader_full[STAGES];
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) leader_full[i] = mapa_u32(smem_u32(&full_bar[i]), 0);
+    if (rank == 0 && lane == 0) nxt = atomicAdd(p.counter, 1u);
+    for (int it = 0;; ++it) {
+      uint32_t item;
+      if (rank == 0) {
+        const int slot = it % SCHED_SLOTS;
+        const uint32_t sph = (it / SCHED_SLOTS) & 1u;
+        const unsigned cur = __shfl_sync(0xffffffffu, nxt, 0);
+        item = cur < p.total_items ? decode_item(p, cur, band_cursor) : ITEM_DONE;
+        mbar_wait(&sempty_bar[slot], sph ^ 1u, 5);
+        if (lane == 0) {
+          sched_item[slot] = item;
+          st_shared_cluster_u32(mapa_u32(smem_u32(&sched_item[slot]), 1), item);
+          mbar_arrive(&sfull_bar[slot]);
+          mbar_arrive_release_cluster(mapa_u32(smem_u32(&sfull_bar[slot]), 1));
+          if (item != ITEM_DONE) nxt = atomicAdd(p.counter, 1u);  // result is needed only at the top of the next iteration
+        }
+        __syncwarp();
+      } else {
+        item = ring_read(it);
+      }
+      if (item == ITEM_DONE) break;
+      const int layer = item & 7u, nt = (item >> 3) & 31u, mt = item >> 8;
+      const StackLayer& L = p.L[layer];
+      const int bke = (kAllTf32 || L.tf32) ? 32 : 64;  // elements per 128-byte chunk
+      const int m0 = mt * BM + static_cast<int>(rank) * BM_CTA;
+      const int n0 = nt * BN + static_cast<int>(rank) * BN_CTA;
+      if (layer > 0) {
+        // the input rows of this tile (and the rows its own output will overwrite two layers later) are complete
+        const unsigned target = static_cast<unsigned>(p.L[layer - 1].n_tiles) * 2u * EPI_WARPS;
+        const unsigned* f = p.ready + static_cast<size_t>(layer - 1) * p.m_tiles + mt;
+        // reads: this CTA's 128 rows + the taps' reach (rank 1 runs into tile mt+1); writes: rows whose old contents tiles
+        // mt-1 and mt of the previous layer were reading
+        const int d0 = mt > 0 ? -1 : 0, d1 = (rank == 1 && mt + 1 < p.m_tiles) ? 1 : 0;
+        uint32_t spins = 0;
+        for (int d = d0; d <= d1; ++d) {
+          while (ld_acquire_gpu_u32(f + d) < target) {
+            if (++spins > (1u << 24)) {
+              atomicExch(&g_watchdog_code, 7u);
+              __trap();
+            }
+          }
+        }
+        fence_proxy_async_all();
+      }
+      const CUtensorMap* ma = &maps.a[layer];
+      const CUtensorMap* mb = &maps.b[layer];
+      const int kblocks = L.taps * L.cpt;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int tap = kb / L.cpt;
+        const int ch = kb - tap * L.cpt;
+        if (!rdy) mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+        const int arow = m0 + L.tap_off[tap];
+        int stage_n = stage + 1;
+        uint32_t phase_n = phase;
+        if (stage_n == STAGES) { stage_n = 0; phase_n ^= 1u; }
+        uint32_t lf = leader_full[0];
+#pragma unroll
+        for (int i = 1; i < STAGES; ++i) lf = (stage == i) ? leader_full[i] : lf;
+        const uint32_t sa = smem_u32(base + stage * STAGE_BYTES);
+        rdy = tma_step_pair(elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, smem_u32(&full_bar[stage]), lf, 2 * STAGE_BYTES, sa, ma, ch * bke,
+                            arow, p.pol_a, sa + A_BYTES, mb, kb * bke, n0, p.pol_b, smem_u32(&empty_bar[stage_n]), phase_n ^ 1u);
+        stage = stage_n;
+        phase = phase_n;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0, rdy = 0;
+      for (int it = 0;; ++it) {
+        const uint32_t item = ring_read(it);
+        if (item == ITEM_DONE) break;
+        const StackLayer& L = p.L[item & 7u];
+        const int buf = it & 1;
+        const uint32_t use = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], use ^ 1u, 2);  // both CTAs' epilogues have drained this accumulator buffer
+        const uint32_t d = tmem_base + buf * BN;
+        const int kblocks = L.taps * L.cpt;
+        if (kAllTf32 || L.tf32) mma_tile<true>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy);
+        else mma_tile<false>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy);
+        if (elect_one()) umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, 128 rows each)
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int cbeg = ((warp - 2) >> 2) * (BN / 2);  // this warp's half of the tile's columns
+    const int cend = cbeg + BN / 2;
+    uint8_t* out_stage = epi_smem + (warp - 2) * (OUT_BUFS * OUT_BUF_BYTES);  // 2 x (32 rows x 128 bytes); also the pool transpose tile
+    constexpr int OUT_ES = kAllTf32 ? 4 : 2;
+    constexpr int GROUP_COLS = 128 / OUT_ES;         // columns per TMA-store box (128 bytes per row)
+    constexpr int CHUNKS = GROUP_COLS / 32;          // tcgen05.ld chunks per box
+    constexpr int BOXES = (BN / 2) / GROUP_COLS;     // boxes (= bulk groups) per tile and warp
+    int store_seq = 0;
+    unsigned* pend = nullptr;  // ready counter of the last stored tile whose completion has not been published yet (warp-uniform)
+    // Publish `pend`: lane 0 owns the warp's bulk groups; once they are complete the tile's rows are in global memory.
+    auto flush = [&]() {
+      if (lane == 0) {
+        tma_store_wait_all();
+        fence_proxy_async_all();
+        red_release_gpu_add_u32(pend, 1u);
+      }
+      pend = nullptr;
+    };
+    for (int it = 0;; ++it) {
+      // Never sleep on future work with an unpublished tile: a consumer of that tile may be what the future work waits for.
+      {
+        const int slot = it % SCHED_SLOTS;
+        const uint32_t sph = (it / SCHED_SLOTS) & 1u;
+        if (pend && !(rank == 0 ? mbar_try_wait(&sfull_bar[slot], sph) : mbar_try_wait_cluster(&sfull_bar[slot], sph))) flush();
+      }
+      const uint32_t item = ring_read(it);
+      if (item == ITEM_DONE) break;
+      const int layer = item & 7u, nt = (item >> 3) & 31u, mt = item >> 8;
+      const StackLayer& L = p.L[layer];
+      const int m0 = mt * BM + static_cast<int>(rank) * BM_CTA;
+      const int n0 = nt * BN;
+      const int buf = it & 1;
+      const uint32_t use = (it >> 1) & 1;
+      if (pend && !mbar_try_wait(&tfull_bar[buf], use)) flush();
+      mbar_wait(&tfull_bar[buf], use, 4);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const int row0 = m0 + q * 32;
+      bool released = false;
+      auto release_tmem = [&]() {  // right after this warp's LAST tcgen05.ld of the tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+        released = true;
+      };
+
+      if (layer == p.n_layers - 1) {
+        // last layer: statistics-pooling partials, nothing stored, nobody waits for this tile
+        if (lane == 0) tma_store_wait_read<0>();  // the transpose tile aliases the store staging boxes
+        __syncwarp();
+        const PoolArgs pa{p.rows, L.n, L.bias, p.row_utt, p.blk_slot_base, p.part};
+        pool_epilogue_tile(pa, tbase, row0, n0, cbeg, cend, reinterpret_cast<float*>(out_stage), lane, release_tmem);
+        if (!released) release_tmem();
+        if (pend) flush();  // its stores were issued a whole tile ago
+      } else {
+        const CUtensorMap* my = &maps.y[layer];
+#pragma unroll 1
+        for (int bx = 0; bx < BOXES; ++bx) {
+          const int c = cbeg + bx * GROUP_COLS;
+          uint8_t* ob = out_stage + (store_seq % OUT_BUFS) * OUT_BUF_BYTES;
+          if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();  // the store that last used this box has read it
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < CHUNKS; ++cc) {
+            const int col0 = n0 + c + cc * 32;
+            uint32_t v[32];
+            tmem_ld_32x32(tbase + c + cc * 32, v);
+            tmem_ld_wait();
+            if (bx == BOXES - 1 && cc == CHUNKS - 1) release_tmem();
+            // r = relu(acc + bias') — every BatchNorm is folded forward into the next layer's weights (xvector.py)
+            float o[32];
+            const float4* bp = reinterpret_cast<const float4*>(L.bias + col0);
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              const float4 bb = __ldg(bp + (j4 >> 2));
+              const float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 0]), __uint_as_float(v[j4 + 1])), make_float2(bb.x, bb.y));
+              const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), make_float2(bb.z, bb.w));
+              o[j4 + 0] = a.x; o[j4 + 1] = a.y; o[j4 + 2] = d.x; o[j4 + 3] = d.y;
+            }
+            // row `lane` of the box, 16-byte pieces XOR-swizzled like CU_TENSOR_MAP_SWIZZLE_128B expects
+            uint8_t* orow = ob + lane * 128;
+            if constexpr (!kAllTf32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 w;
+                w.x = pack_bf16x2_relu(o[8 * j + 0], o[8 * j + 1]);
+                w.y = pack_bf16x2_relu(o[8 * j + 2], o[8 * j + 3]);
+                w.z = pack_bf16x2_relu(o[8 * j + 4], o[8 * j + 5]);
+                w.w = pack_bf16x2_relu(o[8 * j + 6], o[8 * j + 7]);
+                const int piece = cc * 4 + j;
+                *reinterpret_cast<uint4*>(orow + ((piece ^ (lane & 7)) << 4)) = w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w = make_float4(fmaxf(o[4 * j], 0.f), fmaxf(o[4 * j + 1], 0.f), fmaxf(o[4 * j + 2], 0.f), fmaxf(o[4 * j + 3], 0.f));
+                *reinterpret_cast<float4*>(orow + ((j ^ (lane & 7)) << 4)) = w;
+              }
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            if (row0 < p.rows) tma_store_2d(my, ob, n0 + c, row0, p.pol_y);  // rows past the matrix are clipped
+            tma_store_commit();  // one group per box, also when nothing was stored, so that the group arithmetic below holds
+          }
+          ++store_seq;
+        }
+        if (pend) {  // the previous stored tile's groups are older than this tile's BOXES groups
+          if (lane == 0) {
+            tma_store_wait_done<BOXES>();
+            fence_proxy_async_all();
+            red_release_gpu_add_u32(pend, 1u);
+          }
+        }
+        pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
+      }
+    }
+    if (pend) flush();
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading our smem / signalling our barriers until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// Band height: a band-layer should hold >= 2 waves of work items so that an item's inputs are (almost always) complete by the
+// time it is drawn, and the band table must fit the kernel parameters.  XVEC_BAND overrides (developer A/B switch).
+static int pick_band(int m_tiles, int n_layers, int pairs) {
+  const char* e = getenv("XVEC_BAND");
+  const int env = e ? atoi(e) : 0;
+  int band = env > 0 ? env : pairs;
+  if (band < n_layers) band = n_layers;
+  while ((m_tiles + n_layers - 1 + band - 1) / band > XVEC_STACK_MAX_BANDS) band *= 2;
+  return band;
+}
+
+int64_t stack_ctrl_bytes(int64_t rows, int n_layers) {
+  if (rows <= 0 || n_layers < 2) return 0;
+  const int64_t m_tiles = (rows + BM - 1) / BM;
+  return 128 + (n_layers - 1) * m_tiles * 4;
+}
+
+template <bool kAllTf32>
+static int launch_stack(const StackMaps& maps, const StackParams& p, int grid, cudaStream_t st) {
+  static bool configured[64] = {};
+  constexpr int smem = stack_smem_bytes();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tdnn_stack_kernel<kAllTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tdnn_stack_kernel<kAllTf32>, maps, p);
+  if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "tdnn_stack_kernel launch: %s", cudaGetErrorString(e));
+  return XVEC_OK;
+}
+
+bool stack_supported(const XvecLayerDesc* tdnn, int n_tdnn, int64_t rows) {
+  if (n_tdnn < 2 || n_tdnn > XVEC_MAX_STACK || rows <= 0 || rows > 0x7fffff00LL) return false;
+  if (tdnn[0].dtype != XVEC_F32) return false;
+  for (int i = 0; i < n_tdnn; ++i) {
+    if (tdnn[i].taps < 1 || tdnn[i].taps > XVEC_MAX_TAPS) return false;
+    if (i > 0 && (tdnn[i].dtype != tdnn[1].dtype || tdnn[i].cin != tdnn[i - 1].n)) return false;
+    if (i + 1 < n_tdnn && (tdnn[i].n % BN != 0 || !tdnn[i].bias_dev)) return false;  // stored layers: full tiles, bias vector
+    if ((tdnn[i].n + BN - 1) / BN > 31) return false;
+    int max_off = 0;
+    for (int j = 0; j < tdnn[i].taps; ++j) {
+      if (tdnn[i].tap_offsets[j] < 0) return false;
+      if (tdnn[i].tap_offsets[j] > max_off) max_off = tdnn[i].tap_offsets[j];
+    }
+    if (max_off > BM_CTA) return false;  // a tile reads its own m-tile and the first rows of the next one only
+  }
+  return true;
+}
+
+int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const float* x, int64_t rows, int64_t x_ld, void* act0, void* act1,
+                   int64_t act_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part, void* ctrl, int64_t ctrl_bytes,
+                   void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!stack_supported(tdnn, n_tdnn, rows)) return set_error(XVEC_E_ARG, "layer stack is not supported by the fused stack kernel");
+  if (!x || !act0 || !act1 || !row_utt || !blk_slot_base || !part || !ctrl) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (ctrl_bytes < stack_ctrl_bytes(rows, n_tdnn) || (reinterpret_cast<uintptr_t>(ctrl) & 127u))
+    return set_error(XVEC_E_ARG, "ctrl_dev must be 128-byte aligned and hold xvec_stack_ctrl_bytes() bytes");
+  const bool all_tf32 = tdnn[1].dtype == XVEC_F32;
+  const int act_dtype = tdnn[1].dtype;
+  StackMaps local_maps;
+  StackParams p{};
+  p.rows = static_cast<int>(rows);
+  p.m_tiles = static_cast<int>((rows + BM - 1) / BM);
+  p.n_layers = n_tdnn;
+  void* act[2] = {act0, act1};
+  const void* h = x;
+  int64_t h_ld = x_ld;
+  int h_dtype = XVEC_F32;
+  int64_t items_per_mtile = 0;
+  for (int l = 0; l < n_tdnn; ++l) {
+    const XvecLayerDesc& d = tdnn[l];
+    StackLayer& L = p.L[l];
+    const int bke = d.dtype == XVEC_F32 ? 32 : 64;
+    L.n = d.n;
+    L.n_tiles = (d.n + BN - 1) / BN;
+    L.taps = d.taps;
+    L.cpt = (d.cin + bke - 1) / bke;
+    L.tf32 = d.dtype == XVEC_F32 ? 1 : 0;
+    for (int j = 0; j < d.taps; ++j) L.tap_off[j] = d.tap_offsets[j];
+    L.bias = d.bias_dev;
+    if (reinterpret_cast<uintptr_t>(d.bias_dev) & 15u) return set_error(XVEC_E_ARG, "bias must be 16-byte aligned");
+    items_per_mtile += L.n_tiles;
+    rc = make_tmap_2d(&local_maps.a[l], h, h_dtype, static_cast<uint64_t>(d.cin), static_cast<uint64_t>(rows), static_cast<uint64_t>(h_ld),
+                      bke, BM_CTA);
+    if (rc) return rc;
+    const uint64_t kpad = static_cast<uint64_t>(d.taps) * L.cpt * bke;
+    rc = make_tmap_2d(&local_maps.b[l], d.w_packed_dev, d.dtype, kpad, static_cast<uint64_t>(L.n_tiles) * BN, kpad, bke, BN_CTA);
+    if (rc) return rc;
+    if (l + 1 < n_tdnn) {
+      rc = make_tmap_2d(&local_maps.y[l], act[l & 1], act_dtype, static_cast<uint64_t>(d.n), static_cast<uint64_t>(rows),
+                        static_cast<uint64_t>(act_ld), static_cast<uint32_t>(128 / (act_dtype == XVEC_BF16 ? 2 : 4)), 32);
+      if (rc) return rc;
+      h = act[l & 1];
+      h_ld = act_ld;
+      h_dtype = act_dtype;
+    } else {
+      local_maps.y[l] = local_maps.a[l];  // unused
+    }
+  }
+  for (int l = n_tdnn; l < XVEC_MAX_STACK; ++l) {
+    local_maps.a[l] = local_maps.a[0];
+    local_maps.b[l] = local_maps.b[0];
+    local_maps.y[l] = local_maps.a[0];
+  }
+  const int max_pairs = num_sms() / 2;
+  p.band = pick_band(p.m_tiles, n_tdnn, max_pairs);
+  p.n_bands = (p.m_tiles + n_tdnn - 1 + p.band - 1) / p.band;
+  unsigned acc = 0;
+  for (int b = 0; b < p.n_bands; ++b) {
+    p.band_first[b] = acc;
+    for (int l = 0; l < n_tdnn; ++l) {
+      int lo;
+      acc += static_cast<unsigned>(band_layer_range(p.band, p.m_tiles, b, l, &lo)) * p.L[l].n_tiles;
+    }
+  }
+  p.band_first[p.n_bands] = acc;
+  if (static_cast<int64_t>(acc) != items_per_mtile * p.m_tiles) return set_error(XVEC_E_ARG, "internal: band table does not cover the stack");
+  p.total_items = acc;
+  p.counter = static_cast<unsigned*>(ctrl);
+  p.ready = reinterpret_cast<unsigned*>(static_cast<char*>(ctrl) + 128);
+  p.row_utt = row_utt;
+  p.blk_slot_base = blk_slot_base;
+  p.part = part;
+  l2_policies(&p.pol_a, &p.pol_b, &p.pol_y);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(ctrl, 0, static_cast<size_t>(stack_ctrl_bytes(rows, n_tdnn)), st);
+  if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaMemsetAsync(ctrl): %s", cudaGetErrorString(e));
+  const int64_t pairs = static_cast<int64_t>(acc) < max_pairs ? acc : max_pairs;
+  const int grid = 2 * static_cast<int>(pairs);
+  return all_tf32 ? launch_stack<true>(local_maps, p, grid, st) : launch_stack<false>(local_maps, p, grid, st);
+}
+
+}  // namespace xvec

@@ -107,6 +107,27 @@ def tdnn_pool_fused(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
     return part
 
 
+def tdnn_stack(layer_descs, n_layers: int, x: torch.Tensor, act0: torch.Tensor, act1: torch.Tensor, row_utt: torch.Tensor,
+               blk_slot_base: torch.Tensor, part: torch.Tensor, ctrl: torch.Tensor):
+    """All TDNN layers of the stack in one persistent launch (xvec_tdnn_stack): layers 0..n-2 ping-pong through act0/act1,
+    the last one fills the pooling partials `part`.  layer_descs: ctypes array of _lib.LayerDesc (packed operands)."""
+    _require_cuda(x, act0, act1, row_utt, blk_slot_base, part, ctrl)
+    lib = _lib.load()
+    x_ld = _rowmajor_2d(x, "x")
+    act_ld = _rowmajor_2d(act0, "act0")
+    rows = x.shape[0]
+    if x.dtype != torch.float32 or act0.dtype != act1.dtype or _rowmajor_2d(act1, "act1") != act_ld:
+        raise ValueError("x must be float32; act0 / act1 must share dtype and row stride")
+    if act0.shape[0] < rows or act1.shape[0] < rows:
+        raise ValueError("activation buffers are too small for this frame matrix")
+    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * 8 or not part.is_contiguous():
+        raise ValueError("pooling bookkeeping arrays are too small for this frame matrix")
+    with torch.cuda.device(x.device):
+        check(lib.xvec_tdnn_stack(layer_descs, n_layers, ptr(x), rows, x_ld, ptr(act0), ptr(act1), act_ld, ptr(row_utt), ptr(blk_slot_base),
+                                  ptr(part), ptr(ctrl), ctrl.numel(), stream_ptr()))
+    return part
+
+
 def pool_finalize(part: torch.Tensor, slot_start: torch.Tensor, n_rows: torch.Tensor, p: int, bn_scale=None, bn_shift=None,
                   out: torch.Tensor | None = None, out_lp: torch.Tensor | None = None):
     """[mean || unbiased std] per utterance from partial sums; returns float32 (n_utts, 2p)."""

@@ -5,8 +5,9 @@ Same constructor keywords, same sub-module names and state_dict keys (so a refer
 ``test_step`` semantics in eval mode.  The Lightning trainer, dataset and optimiser are out of scope.
 
 Pipeline of extract_x_vec on one flat frame matrix (rows = sum of utterance lengths):
-    TDNN1..4  xvec_tdnn_layer        tcgen05 GEMM, TMA-shifted frame windows, bias+ReLU+BN epilogue
-    TDNN5     xvec_tdnn_pool_fused   same GEMM, epilogue = per-utterance column sums (activation never stored)
+    TDNN1..5  xvec_tdnn_stack        ONE persistent launch: tcgen05 GEMM tiles of all five layers drawn from a work queue,
+                                     TMA-shifted frame windows, bias+ReLU epilogue (BN folded forward); TDNN5's epilogue =
+                                     per-utterance column sums (its activation is never stored)
     pooling   xvec_pool_finalize     fixed-order fp64 reduction -> [mean || std], BN5 folded through
     segment6/7  xvec_tdnn_layer (taps = 1)
 """
@@ -78,7 +79,7 @@ class _Scratch:
         per16 = 16 // torch.empty((), dtype=act_dtype).element_size()
         self.ld = (max(widths) + per16 - 1) // per16 * per16
         self.rows_cap = self.slots_cap = self.utts_cap = 0
-        self.act = self.part = self.pooled = self.pooled_lp = None
+        self.act = self.part = self.pooled = self.pooled_lp = self.ctrl = None
         self.fc_tmp = self.ws = None
         self.ws_for = None
 
@@ -86,6 +87,11 @@ class _Scratch:
         if rows > self.rows_cap:
             self.rows_cap = max(rows, int(self.rows_cap * 1.25))
             self.act = [torch.empty((self.rows_cap, self.ld), dtype=self.act_dtype, device=self.device) for _ in range(2)]
+            # work-item counter + per-tile completion flags of xvec_tdnn_stack (zeroed by the call itself)
+            need = _lib.load().xvec_stack_ctrl_bytes(self.rows_cap, _lib.MAX_STACK)
+            self.ctrl = torch.empty(need + 128, dtype=torch.uint8, device=self.device)
+            off = (-self.ctrl.data_ptr()) % 128
+            self.ctrl = self.ctrl[off: off + need]
         if n_slots > self.slots_cap:
             self.slots_cap = max(n_slots, int(self.slots_cap * 1.25))
             self.part = torch.empty((self.slots_cap, 2, self.pool_dim), dtype=torch.float32, device=self.device)
@@ -176,6 +182,14 @@ class XVectorModel(nn.Module):
             sc = _Scratch(dev, self.act_dtype, [l.output_size for l in layers[:-1]], layers[-1].output_size)
             self._scratch[key] = sc
         return sc
+
+    def _stack_kernel_ok(self) -> bool:
+        """Limits of xvec_tdnn_stack (include/xvec_b200.h): stored layers are whole 256-channel tiles, chained widths."""
+        layers = list(self.time_context_layers)
+        return (2 <= len(layers) <= _lib.MAX_STACK
+                and all(l.output_size % _lib.TILE_N == 0 for l in layers[:-1])
+                and all(a.output_size == b.input_size for a, b in zip(layers[:-1], layers[1:]))
+                and all(tap_offsets(l.context)[-1] <= 128 for l in layers))
 
     def _stack_params(self):
         """Packed operands of the five TDNN layers for the fused pipeline, with every layer's eval-mode BatchNorm folded
@@ -275,22 +289,27 @@ class XVectorModel(nn.Module):
             raise ValueError("sum(lengths) does not match the number of rows")
         sc = self._scratch_for(slot)
         sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
-        layers = list(self.time_context_layers)
         if flat_x.dtype != torch.float32:
             flat_x = flat_x.float()
-        stack, (scale5, shift5) = self._stack_params()
-        h = _aligned_rows(flat_x)  # layer 1 always reads float32 frames (TF32 math): no cast pass over the input
-        for i, layer in enumerate(layers[:-1]):
-            w, bias, offs = stack[i]
-            out = sc.act[i & 1][: lay.rows, : layer.output_size]
-            h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True, out=out, cin=layer.input_size)
-        last = layers[-1]
-        w, bias, offs = stack[-1]
+        pipe = self._pipeline()
+        last = self.time_context_layers[-1]
         part = sc.part[: lay.n_slots]
         pooled = sc.pooled[: lay.n_utts]
         pooled_lp = None if sc.pooled_lp is None else sc.pooled_lp[: lay.n_utts]
-        ops.tdnn_pool_fused(h, w, last.output_size, offs, bias, lay.row_utt, lay.blk_slot_base, part)
-        ops.pool_finalize(part, lay.utt_slot_start, lay.n_pool, last.output_size, scale5, shift5, out=pooled, out_lp=pooled_lp)
+        x = _aligned_rows(flat_x)  # layer 1 always reads float32 frames (TF32 math): no cast pass over the input
+        if self._stack_kernel_ok():
+            ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], x, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
+        else:  # layer widths the one-launch stack kernel does not take: one launch per layer
+            layers = list(self.time_context_layers)
+            stack = pipe["keep"][0]
+            h = x
+            for i, layer in enumerate(layers[:-1]):
+                w, bias, offs = stack[i]
+                h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True,
+                                        out=sc.act[i & 1][: lay.rows, : layer.output_size], cin=layer.input_size)
+            w, bias, offs = stack[-1]
+            ops.tdnn_pool_fused(h, w, last.output_size, offs, bias, lay.row_utt, lay.blk_slot_base, part)
+        ops.pool_finalize(part, lay.utt_slot_start, lay.n_pool, last.output_size, pipe["scale5"], pipe["shift5"], out=pooled, out_lp=pooled_lp)
         return pooled, pooled_lp
 
 
@@ -304,7 +323,8 @@ class XVectorModel(nn.Module):
     def extract_x_vec_flat(self, flat_x: torch.Tensor, lengths, slot: int = 0) -> torch.Tensor:
         """Ragged extraction: flat (sum(lengths), input_size) frames -> float32 (len(lengths), x_vector_size).
         `slot` selects an independent scratch set so that calls on different CUDA streams can overlap.
-        The whole path is ONE C-ABI call (xvec_extract_forward) that enqueues its 8 kernels on the current stream."""
+        The whole path is ONE C-ABI call (xvec_extract_forward) that enqueues its kernels on the current stream: the
+        persistent TDNN-stack kernel (all five layers + pooling partials), the pooling finalize and the segment layer(s)."""
         self._check_eval()
         if not flat_x.is_cuda:
             raise ValueError("xvec_b200 has no CPU path: move the input (and the model) to a CUDA device")
@@ -328,7 +348,7 @@ class XVectorModel(nn.Module):
                 pipe["tdnn"], pipe["n_tdnn"], p(x), lay.rows, x.stride(0), p(sc.act[0]), p(sc.act[1]), sc.ld, p(lay.row_utt),
                 p(lay.blk_slot_base), p(lay.utt_slot_start), p(lay.n_pool), lay.n_utts, p(sc.part), p(pipe["scale5"]), p(pipe["shift5"]),
                 p(sc.pooled), p(sc.pooled_lp), pipe["fc"], pipe["n_fc"], p(sc.fc_tmp), p(sc.ws),
-                0 if sc.ws is None else sc.ws.numel(), p(out), out.stride(0), _lib.stream_ptr()))
+                0 if sc.ws is None else sc.ws.numel(), p(out), out.stride(0), p(sc.ctrl), sc.ctrl.numel(), _lib.stream_ptr()))
         return out
 
     # ------------------------------------------------------------------ reference surface

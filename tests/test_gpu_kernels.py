@@ -196,3 +196,46 @@ def test_argument_errors(xb):
         xb.ops.tdnn_layer_flat(x[:, 1:], wp, 511, [0], cin=511)    # misaligned rows
     with pytest.raises(ValueError):
         xb.TdnnLayer(24, 32, [-1, 0, 2]).cuda().eval()(torch.randn(1, 30, 24, device="cuda"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+@pytest.mark.parametrize("band", [0, 5, 7, 1000])
+def test_stack_kernel_equals_per_layer_launches(xb, state_dict, precision, band, monkeypatch):
+    """xvec_tdnn_stack (one persistent launch, dynamic tile queue, per-tile dependency flags) must reproduce the per-layer
+    launches bit for bit — same tiles, same K order, same epilogues — for every band height of the work-item order."""
+    from xvec_b200 import ops
+    from oracle import xvector_oracle as ox
+    m = xb.XVectorModel(precision=precision)
+    m.load_state_dict(state_dict)
+    m = m.cuda().eval()
+    lens = np.asarray([300] * 9 + [45, 16, 777, 1503, 15, 64, 2200])
+    utts = ox.synth_ragged(lens, seed=7)
+    flat = torch.cat(utts).cuda()
+    lay = m._layout_for(lens)
+    pipe = m._pipeline()
+    stack = pipe["keep"][0]
+    layers = list(m.time_context_layers)
+    sc = m._scratch_for(0)
+    sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
+    h = flat
+    acts = []
+    for i, layer in enumerate(layers[:-1]):
+        w, bias, offs = stack[i]
+        h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True, out_dtype=m.act_dtype, cin=layer.input_size)
+        acts.append(h)
+    w, bias, offs = stack[-1]
+    part_ref = torch.zeros((lay.n_slots, 2, 1500), device="cuda")
+    ops.tdnn_pool_fused(h, w, 1500, offs, bias, lay.row_utt, lay.blk_slot_base, part_ref)
+    if band:
+        monkeypatch.setenv("XVEC_BAND", str(band))
+    for rep in range(3):  # repeated launches reuse (and re-zero) the same control block
+        part = torch.zeros((lay.n_slots, 2, 1500), device="cuda")
+        sc.act[0].zero_(); sc.act[1].zero_()
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], flat, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
+        torch.cuda.synchronize()
+        assert torch.equal(part, part_ref)
+        # layer 3 / layer 4 outputs are what is left in the ping-pong buffers
+        assert torch.equal(sc.act[0][: lay.rows, :512], acts[2])
+        assert torch.equal(sc.act[1][: lay.rows, :512], acts[3])
+    assert xb._lib.load().xvec_watchdog_code() == 0
