@@ -199,8 +199,9 @@ def run_b200(args, rank, world, local_rank):
     dev_ms = e_beg.elapsed_time(e_end)
 
     # ---- end to end through the host API (pinned host -> H2D -> kernels -> D2H), double-buffered
-    hx = xvec_b200.HostExtractor(model, n_slots=3)
-    for i in range(6):
+    N_SLOTS = 6
+    hx = xvec_b200.HostExtractor(model, n_slots=N_SLOTS)
+    for i in range(2 * N_SLOTS):
         hx.result(hx.submit(x_host[i % n_batches], lengths))
     barrier()
     hx.h2d_bytes = hx.d2h_bytes = 0
@@ -211,7 +212,7 @@ def run_b200(args, rank, world, local_rank):
     checksum = 0.0
     for i in range(args.steps):
         tickets.append(hx.submit(x_host[i % n_batches], lengths))
-        if len(tickets) == 3:
+        if len(tickets) == N_SLOTS:
             checksum += float(hx.result(tickets.pop(0))[0, 0])
     while tickets:
         checksum += float(hx.result(tickets.pop(0))[0, 0])
@@ -252,7 +253,7 @@ def run_b200(args, rank, world, local_rank):
                              "2 batches in flight, activations of the two (4 x 78 MB) also exceed the 126 MB L2",
                        "tdnn1": "TF32 math on the float32 MFCCs in both modes"},
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": hx.h2d_bytes // args.steps, "d2h_bytes_per_step": hx.d2h_bytes // args.steps,
-                    "api": "HostExtractor.submit/result (pinned host MFCCs in, pinned host x-vectors out, 3 slots / streams)",
+                    "api": "HostExtractor.submit/result (pinned host MFCCs in, pinned host x-vectors out, 6 slots / streams)",
                     "frames_per_sec": e2e * FRAMES, "checksum": checksum},
             "gpu_launches": args.steps * 4,  # tdnn_stack_kernel, pool_finalize_kernel, tdnn_gemm_kernel (segment6, split-K), splitk_reduce_kernel
             "clocks": clocks,
@@ -369,7 +370,7 @@ def pooling_roofline(model, dev, peaks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])

@@ -4,8 +4,8 @@
 // quantisations (600 tiles on 74 CTA pairs = 8.1 waves).  Here every (layer, 256-frame m-tile, 256-channel n-tile) of the
 // stack is one WORK ITEM of a single launch:
 //
-//   * dynamic tile scheduler: the leader CTA of each pair draws the next item with one atomicAdd on a global counter
-//     (prefetched one tile ahead) and hands it to all warp roles of both CTAs through a small shared-memory ring
+//   * dynamic tile scheduler: a scheduler warp in the leader CTA of each pair draws the next item with one atomicAdd on a global
+//     counter (while the current tile is loading) and hands it to all warp roles of both CTAs through a small shared-memory ring
 //     (mbarrier full/empty, the peer's copy written with st.shared::cluster + release/acquire at cluster scope).  Items are
 //     drawn strictly in order and an item only depends on EARLIER items, so any number of resident CTAs makes progress —
 //     two of these kernels on two streams cannot deadlock each other.
@@ -13,8 +13,9 @@
 //     (layer l+1 tile m reads layer l tiles m-1.. m+1, all in the same or an earlier band).  A band's activations
 //     (band*256 rows x 512 ch) stay in L2 between the layers; short-K / store-bound layers overlap with MMA-bound ones.
 //   * inter-layer dependencies: every epilogue warp adds 1 to ready[layer][m_tile] (red.release.gpu) once its TMA stores of
-//     that tile are COMPLETE (cp.async.bulk.wait_group, deferred so that it never blocks a busy warp); the TMA producer of a
-//     consuming tile spins (ld.acquire.gpu) until the three tiles it touches are complete, then fence.proxy.async.
+//     that tile are COMPLETE (cp.async.bulk.wait_group, deferred so that it never blocks a busy warp); a dependency warp per
+//     CTA runs ahead of the TMA producer, polls (ld.acquire.gpu) the flags of the tiles the next items touch and hands each
+//     item to the producer through an mbarrier, so flag latency and the proxy fence stay off the load path.
 //     The two ping-pong activation buffers are safe: tile (l, m) overwrites rows whose readers (l-1, m-1) and (l-1, m) it
 //     has just waited for.
 //
@@ -28,7 +29,9 @@ namespace xvec {
 constexpr int STACK_STAGES = 5;
 constexpr int SCHED_SLOTS = 8;            // work-item ring between the scheduler and the warp roles
 constexpr uint32_t ITEM_DONE = 0xFFFFFFFFu;
-constexpr int SCHED_CONSUMERS = 2 * EPI_WARPS + 2;  // per slot: leader MMA warp + peer producer + 8 epilogue warps of each CTA
+constexpr int SCHED_CONSUMERS = 2 * EPI_WARPS + 4;  // per slot: both producers, leader MMA warp, peer dependency warp, 8 epilogue warps of each CTA
+constexpr int DEP_WARP = 2 + EPI_WARPS;             // warp 10
+constexpr int STACK_THREADS = GEMM_THREADS + 32;
 
 struct StackLayer {
   int n, n_tiles, taps, cpt;  // K loop = taps * cpt chunks of 128 bytes
@@ -52,6 +55,7 @@ struct StackParams {
   const int* blk_slot_base;
   float* part;
   unsigned long long pol_a, pol_b, pol_y;
+  int dbg;
   unsigned band_first[XVEC_STACK_MAX_BANDS + 1];
 };
 
@@ -76,13 +80,31 @@ __device__ __forceinline__ uint32_t decode_item(const StackParams& p, unsigned i
   return ITEM_DONE;  // unreachable when the host table is consistent
 }
 
+// Developer switches (-DXVEC_DEBUG builds only; XVEC_STACK_DBG): 1 skip the dependency waits, 2 skip the completion
+// signalling (only together with 1), 4 skip the proxy fences (results are then undefined; timing experiments only).
+// Debug builds also accumulate counters in the spare words of the control block (ctrl[1..7], units of 64 cycles):
+// 1 tiles whose dependency warp had to spin on a flag, 2 flag polls, 3 cycles the producer waited for its dependency warp,
+// 4 cycles the scheduler waited to publish,
+// 5 cycles the MMA warp waited for operands, 6 cycles it waited for a free accumulator buffer, 7 cycles epilogue warp 2 waited for tfull.
+#ifdef XVEC_DEBUG
+#define XVEC_SDBG(p, bit) ((p).dbg & (bit))
+#define XVEC_CNT(...) __VA_ARGS__
+#else
+#define XVEC_SDBG(p, bit) 0
+#define XVEC_CNT(...)
+#endif
+
 // K loop of one tile on the MMA warp (leader CTA, warp-uniform; see tdnn_gemm.cu).
 template <bool kTf32>
 __device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* full_bar, uint64_t* empty_bar, uint32_t d, int kblocks, int& stage,
-                                         uint32_t& phase, uint32_t& rdy) {
+                                         uint32_t& phase, uint32_t& rdy, unsigned long long& c_wait) {
   constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
   for (int kb = 0; kb < kblocks; ++kb) {
-    if (!(rdy & 1u)) mbar_wait(&full_bar[stage], phase, 3);
+    if (!(rdy & 1u)) {
+      XVEC_CNT(const long long t0 = clock64();)
+      mbar_wait(&full_bar[stage], phase, 3);
+      XVEC_CNT(c_wait += clock64() - t0;)
+    }
     tc_fence_after();
     const uint32_t a_addr = smem_u32(base + stage * STAGE_BYTES);
     const uint64_t da = umma_desc_sw128(a_addr);
@@ -100,12 +122,12 @@ __device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* full_bar, uint
 constexpr int stack_smem_bytes() { return 1024 + STACK_STAGES * STAGE_BYTES + EPI_WARPS * OUT_BUFS * OUT_BUF_BYTES; }
 
 template <bool kAllTf32>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(STACK_THREADS, 1)
 tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant__ StackParams p) {
   constexpr int STAGES = STACK_STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
-  __shared__ uint64_t sfull_bar[SCHED_SLOTS], sempty_bar[SCHED_SLOTS];
+  __shared__ uint64_t sfull_bar[SCHED_SLOTS], sempty_bar[SCHED_SLOTS], dep_bar[SCHED_SLOTS], credit_bar;
   __shared__ uint32_t sched_item[SCHED_SLOTS];
   __shared__ uint32_t tmem_base_smem;
 
@@ -133,7 +155,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     for (int s = 0; s < SCHED_SLOTS; ++s) {
       mbar_init(&sfull_bar[s], 1);                 // the scheduler's arrive (local in the leader, remote in the peer)
       mbar_init(&sempty_bar[s], SCHED_CONSUMERS);  // every consumer of both CTAs, on the leader's barrier
+      mbar_init(&dep_bar[s], 1);                   // this CTA's dependency warp
     }
+    mbar_init(&credit_bar, 1);  // leader's producer, once per tile
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_pair<TMEM_COLS>(&tmem_base_smem);
@@ -156,58 +180,28 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ scheduler (leader) + TMA producer (both CTAs)
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    // Per tile: read the work item (published by the scheduler warp while the previous tile was loading), check that this
+    // CTA's dependency warp has resolved its inputs, tell the scheduler that the tile has started, then run the K loop.
     int stage = 0;
     uint32_t phase = 0, rdy = 0;
-    int band_cursor = 0;
-    unsigned nxt = 0;  // lane 0 of the leader: the prefetched next item
     uint32_t leader_full[STAGES];
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) leader_full[i] = mapa_u32(smem_u32(&full_bar[i]), 0);
-    if (rank == 0 && lane == 0) nxt = atomicAdd(p.counter, 1u);
+    XVEC_CNT(unsigned long long c_fw = 0, c_pub = 0;)
     for (int it = 0;; ++it) {
-      uint32_t item;
-      if (rank == 0) {
-        const int slot = it % SCHED_SLOTS;
-        const uint32_t sph = (it / SCHED_SLOTS) & 1u;
-        const unsigned cur = __shfl_sync(0xffffffffu, nxt, 0);
-        item = cur < p.total_items ? decode_item(p, cur, band_cursor) : ITEM_DONE;
-        mbar_wait(&sempty_bar[slot], sph ^ 1u, 5);
-        if (lane == 0) {
-          sched_item[slot] = item;
-          st_shared_cluster_u32(mapa_u32(smem_u32(&sched_item[slot]), 1), item);
-          mbar_arrive(&sfull_bar[slot]);
-          mbar_arrive_release_cluster(mapa_u32(smem_u32(&sfull_bar[slot]), 1));
-          if (item != ITEM_DONE) nxt = atomicAdd(p.counter, 1u);  // result is needed only at the top of the next iteration
-        }
-        __syncwarp();
-      } else {
-        item = ring_read(it);
-      }
+      XVEC_CNT(long long t0 = clock64();)
+      const uint32_t item = ring_read(it);
+      XVEC_CNT(c_pub += clock64() - t0; t0 = clock64();)
       if (item == ITEM_DONE) break;
+      mbar_wait(&dep_bar[it % SCHED_SLOTS], (it / SCHED_SLOTS) & 1u, 7);
+      XVEC_CNT(c_fw += clock64() - t0;)
+      if (rank == 0 && lane == 0) mbar_arrive(&credit_bar);  // tile `it` has started: the scheduler may draw item it+1
       const int layer = item & 7u, nt = (item >> 3) & 31u, mt = item >> 8;
       const StackLayer& L = p.L[layer];
       const int bke = (kAllTf32 || L.tf32) ? 32 : 64;  // elements per 128-byte chunk
       const int m0 = mt * BM + static_cast<int>(rank) * BM_CTA;
       const int n0 = nt * BN + static_cast<int>(rank) * BN_CTA;
-      if (layer > 0) {
-        // the input rows of this tile (and the rows its own output will overwrite two layers later) are complete
-        const unsigned target = static_cast<unsigned>(p.L[layer - 1].n_tiles) * 2u * EPI_WARPS;
-        const unsigned* f = p.ready + static_cast<size_t>(layer - 1) * p.m_tiles + mt;
-        // reads: this CTA's 128 rows + the taps' reach (rank 1 runs into tile mt+1); writes: rows whose old contents tiles
-        // mt-1 and mt of the previous layer were reading
-        const int d0 = mt > 0 ? -1 : 0, d1 = (rank == 1 && mt + 1 < p.m_tiles) ? 1 : 0;
-        uint32_t spins = 0;
-        for (int d = d0; d <= d1; ++d) {
-          while (ld_acquire_gpu_u32(f + d) < target) {
-            if (++spins > (1u << 24)) {
-              atomicExch(&g_watchdog_code, 7u);
-              __trap();
-            }
-          }
-        }
-        fence_proxy_async_all();
-      }
       const CUtensorMap* ma = &maps.a[layer];
       const CUtensorMap* mb = &maps.b[layer];
       const int kblocks = L.taps * L.cpt;
@@ -229,26 +223,93 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         phase = phase_n;
       }
     }
+    XVEC_CNT(if (lane == 0) {
+      atomicAdd(p.counter + 3, static_cast<unsigned>(c_fw >> 6));
+      atomicAdd(p.counter + 4, static_cast<unsigned>(c_pub >> 6));
+    })
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0, rdy = 0;
+      unsigned long long c_full = 0, c_tempty = 0;
       for (int it = 0;; ++it) {
         const uint32_t item = ring_read(it);
         if (item == ITEM_DONE) break;
         const StackLayer& L = p.L[item & 7u];
         const int buf = it & 1;
         const uint32_t use = (it >> 1) & 1;
+        XVEC_CNT(const long long t0 = clock64();)
         mbar_wait(&tempty_bar[buf], use ^ 1u, 2);  // both CTAs' epilogues have drained this accumulator buffer
+        XVEC_CNT(c_tempty += clock64() - t0;)
         const uint32_t d = tmem_base + buf * BN;
         const int kblocks = L.taps * L.cpt;
-        if (kAllTf32 || L.tf32) mma_tile<true>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy);
-        else mma_tile<false>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy);
+        if (kAllTf32 || L.tf32) mma_tile<true>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy, c_full);
+        else mma_tile<false>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy, c_full);
         if (elect_one()) umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
         __syncwarp();
       }
+      XVEC_CNT(if (lane == 0) {
+        atomicAdd(p.counter + 5, static_cast<unsigned>(c_full >> 6));
+        atomicAdd(p.counter + 6, static_cast<unsigned>(c_tempty >> 6));
+      })
     }
+  } else if (warp == DEP_WARP) {
+    // ------------------------------------------------------------------ scheduler (leader) + dependency warp (both CTAs)
+    // Leader: draws work items (atomicAdd on the global counter), decodes them and publishes them in the ring of both CTAs —
+    // item it+1 as soon as the producer has started tile `it` (credit_bar), so a pair never holds more than one item it has
+    // not begun (a deeper run-ahead would only lengthen the tail of the launch).
+    // Both CTAs: resolve the inter-layer dependencies of every item ahead of the producer: lanes 0..2 poll (ld.acquire.gpu)
+    // the flags of the tiles the item touches — reads: this CTA's 128 rows + the taps' reach (rank 1 runs into tile mt+1);
+    // writes: rows whose old contents (two layers back, same ping-pong buffer) tiles mt-1 and mt of the previous layer were
+    // reading — then fence.proxy.async (flag in the generic proxy -> tile data in the async proxy), one arrive on dep_bar.
+    XVEC_CNT(unsigned long long c_spun = 0, c_polls = 0;)
+    int band_cursor = 0;
+    for (int it = 0;; ++it) {
+      uint32_t item;
+      if (rank == 0) {
+        const int slot = it % SCHED_SLOTS;
+        const uint32_t sph = (it / SCHED_SLOTS) & 1u;
+        if (it > 0) mbar_wait(&credit_bar, (it - 1) & 1u, 8);
+        unsigned raw = 0;
+        if (lane == 0) raw = atomicAdd(p.counter, 1u);
+        raw = __shfl_sync(0xffffffffu, raw, 0);
+        item = raw < p.total_items ? decode_item(p, raw, band_cursor) : ITEM_DONE;
+        mbar_wait(&sempty_bar[slot], sph ^ 1u, 5);
+        if (lane == 0) {
+          sched_item[slot] = item;
+          st_shared_cluster_u32(mapa_u32(smem_u32(&sched_item[slot]), 1), item);
+          mbar_arrive(&sfull_bar[slot]);
+          mbar_arrive_release_cluster(mapa_u32(smem_u32(&sfull_bar[slot]), 1));
+        }
+        __syncwarp();
+      } else {
+        item = ring_read(it);
+      }
+      if (item == ITEM_DONE) break;
+      const int layer = item & 7u, mt = item >> 8;
+      if (layer > 0 && !XVEC_SDBG(p, 1)) {
+        const unsigned target = static_cast<unsigned>(p.L[layer - 1].n_tiles) * 2u * EPI_WARPS;
+        const int d = lane - 1;  // lanes 0..2 -> tiles mt-1, mt, mt+1
+        const bool mine = lane < 3 && mt + d >= 0 && mt + d < p.m_tiles && (d < 1 || rank == 1);
+        const unsigned* f = p.ready + static_cast<size_t>(layer - 1) * p.m_tiles + (mine ? mt + d : mt);
+        uint32_t spins = 0;
+        while (__any_sync(0xffffffffu, mine && ld_acquire_gpu_u32(f) < target)) {
+          if (++spins > (1u << 24)) {
+            atomicExch(&g_watchdog_code, 7u);
+            __trap();
+          }
+        }
+        XVEC_CNT(c_polls += spins; c_spun += spins ? 1 : 0;)
+        if (!XVEC_SDBG(p, 4)) fence_proxy_async_all();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dep_bar[it % SCHED_SLOTS]);
+    }
+    XVEC_CNT(if (lane == 0) {
+      atomicAdd(p.counter + 1, static_cast<unsigned>(c_spun));
+      atomicAdd(p.counter + 2, static_cast<unsigned>(c_polls));
+    })
   } else {
     // ------------------------------------------------------------------ epilogue warps (both CTAs, 128 rows each)
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
@@ -263,9 +324,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     unsigned* pend = nullptr;  // ready counter of the last stored tile whose completion has not been published yet (warp-uniform)
     // Publish `pend`: lane 0 owns the warp's bulk groups; once they are complete the tile's rows are in global memory.
     auto flush = [&]() {
-      if (lane == 0) {
+      if (lane == 0 && !XVEC_SDBG(p, 2)) {
         tma_store_wait_all();
-        fence_proxy_async_all();
+        if (!XVEC_SDBG(p, 4)) fence_proxy_async_all();
         red_release_gpu_add_u32(pend, 1u);
       }
       pend = nullptr;
@@ -275,7 +336,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       {
         const int slot = it % SCHED_SLOTS;
         const uint32_t sph = (it / SCHED_SLOTS) & 1u;
-        if (pend && !(rank == 0 ? mbar_try_wait(&sfull_bar[slot], sph) : mbar_try_wait_cluster(&sfull_bar[slot], sph))) flush();
+        if (pend && !mbar_test_wait(&sfull_bar[slot], sph)) flush();
       }
       const uint32_t item = ring_read(it);
       if (item == ITEM_DONE) break;
@@ -285,7 +346,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       const int n0 = nt * BN;
       const int buf = it & 1;
       const uint32_t use = (it >> 1) & 1;
-      if (pend && !mbar_try_wait(&tfull_bar[buf], use)) flush();
+      if (pend && !mbar_test_wait(&tfull_bar[buf], use)) flush();
       mbar_wait(&tfull_bar[buf], use, 4);
       tc_fence_after();
       const uint32_t tbase = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -361,9 +422,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
           ++store_seq;
         }
         if (pend) {  // the previous stored tile's groups are older than this tile's BOXES groups
-          if (lane == 0) {
+          if (lane == 0 && !XVEC_SDBG(p, 2)) {
             tma_store_wait_done<BOXES>();
-            fence_proxy_async_all();
+            if (!XVEC_SDBG(p, 4)) fence_proxy_async_all();
             red_release_gpu_add_u32(pend, 1u);
           }
         }
@@ -384,12 +445,14 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// Band height: a band-layer should hold >= 2 waves of work items so that an item's inputs are (almost always) complete by the
-// time it is drawn, and the band table must fit the kernel parameters.  XVEC_BAND overrides (developer A/B switch).
+// Band height.  Producers run 3-4 tiles ahead of the published completions, so an item's inputs are only certain to be
+// complete when they were drawn >= ~4 x pairs items earlier; measured on B200 (256 x 300 frames = 300 m-tiles): band 20 / 37 /
+// 74 / 148 / one band = 1.23 / 0.77 / 0.49 / 0.43 / 0.39 ms.  Hence bands of 8 x pairs m-tiles: short batches run layer after
+// layer, long ones keep >= 16 waves between a tile and its consumers.  XVEC_BAND overrides (developer A/B switch).
 static int pick_band(int m_tiles, int n_layers, int pairs) {
   const char* e = getenv("XVEC_BAND");
   const int env = e ? atoi(e) : 0;
-  int band = env > 0 ? env : pairs;
+  int band = env > 0 ? env : 8 * pairs;
   if (band < n_layers) band = n_layers;
   while ((m_tiles + n_layers - 1 + band - 1) / band > XVEC_STACK_MAX_BANDS) band *= 2;
   return band;
@@ -414,7 +477,7 @@ static int launch_stack(const StackMaps& maps, const StackParams& p, int grid, c
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(STACK_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -523,6 +586,10 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const float* x, int64_
   p.blk_slot_base = blk_slot_base;
   p.part = part;
   l2_policies(&p.pol_a, &p.pol_b, &p.pol_y);
+  {
+    const char* e = getenv("XVEC_STACK_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(ctrl, 0, static_cast<size_t>(stack_ctrl_bytes(rows, n_tdnn)), st);
   if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaMemsetAsync(ctrl): %s", cudaGetErrorString(e));

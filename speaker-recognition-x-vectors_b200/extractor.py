@@ -2,8 +2,10 @@
 test_step/test_epoch_end (main.py:135-146) makes, minus the per-utterance .cpu() round trips.
 
 Each of the `n_slots` slots owns a CUDA stream, a device staging buffer, model scratch and a pinned result buffer, so
-the host->device copy of batch i+1 overlaps the kernels of batch i and the device->host copy of batch i-1 (three slots keep
-the GPU fed while the host is blocked reading a result).
+the host->device copy of batch i+1 overlaps the kernels of batch i and the device->host copy of batch i-1.  The persistent
+TDNN-stack kernel of the next batch takes over the SMs as the current one drains, so the small finalize / segment kernels of a
+batch finish about one step late: six slots (measured on B200: 3 / 4 / 6 slots = 623 k / 678 k / 700 k utt/s) keep the GPU fed
+while the host is blocked reading a result.
 """
 from __future__ import annotations
 
@@ -25,7 +27,7 @@ class _Slot:
 
 
 class HostExtractor:
-    def __init__(self, model, n_slots: int = 3):
+    def __init__(self, model, n_slots: int = 6):
         self.model = model
         self.device = model._device()
         if self.device.type != "cuda":

@@ -6,7 +6,7 @@ m = xvec_b200.XVectorModel(precision="bf16"); m.load_state_dict(ox.make_state_di
 B, T = 256, 300
 x_host = ox.synth_mfcc(1024, T, seed=1).reshape(4, B * T, 24).pin_memory()
 lengths = [T] * B
-for slots in (2, 3, 4, 2, 3):
+for slots in (2, 3, 4, 6, 3):
     hx = xvec_b200.HostExtractor(m, n_slots=slots)
     for i in range(2 * slots): hx.result(hx.submit(x_host[i % 4], lengths))
     torch.cuda.synchronize()

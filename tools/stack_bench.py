@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Times the tdnn_stack_kernel launch alone (CUDA events, back-to-back launches) on the bench workload (256 x 300 frames) for a
+sweep of XVEC_BAND / XVEC_STACK_DBG / XVEC_L2HINT settings.  The DBG switches need the debug library:
+    python speaker-recognition-x-vectors_b200/build.py --debug
+    XVEC_LIB=$PWD/speaker-recognition-x-vectors_b200/libxvec_b200_debug.so python tools/stack_bench.py --dbg 0,1,2,3,4,7
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import xvec_b200
+from xvec_b200 import ops
+from oracle import xvector_oracle as ox
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--frames", type=int, default=300)
+ap.add_argument("--dtype", default="bf16")
+ap.add_argument("--band", default="0")
+ap.add_argument("--dbg", default="0")
+ap.add_argument("--iters", type=int, default=30)
+args = ap.parse_args()
+
+m = xvec_b200.XVectorModel(precision=args.dtype)
+m.load_state_dict(ox.make_state_dict(seed=0))
+m = m.cuda().eval()
+n_res = 24
+x = torch.randn(n_res, args.batch * args.frames, 24, device="cuda")
+lengths = [args.frames] * args.batch
+lay = m._layout_for(lengths)
+sc = m._scratch_for(0)
+sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
+pipe = m._pipeline()
+part = sc.part[: lay.n_slots]
+flops = args.batch * sum(f * (args.frames - l) for f, l in zip([122880, 1572864, 1572864, 524288, 1536000], [4, 8, 14, 14, 14]))
+
+
+def run(iters):
+    evs = []
+    for it in range(iters + 3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], x[it % n_res], sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in evs[3:])
+    return sum(t) / len(t), t[0]
+
+
+for band in args.band.split(","):
+    for dbg in args.dbg.split(","):
+        os.environ["XVEC_BAND"] = band
+        os.environ["XVEC_STACK_DBG"] = dbg
+        avg, best = run(args.iters)
+        cnt = sc.ctrl[:32].view(torch.int32).tolist()
+        extra = ("  counters(spun,polls,fw,pub,mma_full,mma_tempty)=" + str([c for c in cnt[1:7]])) if any(cnt[1:7]) else ""
+        print(f"band={band:>5} dbg={dbg}{extra} avg {avg * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {flops / avg / 1e9:7.1f} TFLOP/s", flush=True)
