@@ -19,8 +19,9 @@
 //     The two ping-pong activation buffers are safe: tile (l, m) overwrites rows whose readers (l-1, m-1) and (l-1, m) it
 //     has just waited for.
 //
-// The mainloop, TMEM double buffering and both epilogues are the ones of tdnn_gemm.cu (gemm_tile.cuh); layer 1 always runs
-// kind::tf32 on the float32 MFCCs, the other layers kind::f16 (bf16) or kind::tf32 (kAllTf32).
+// The mainloop and TMEM double buffering are the ones of tdnn_gemm.cu; layer 1 always runs kind::tf32 on the float32 MFCCs, the
+// other layers kind::f16 (bf16) or kind::tf32 (kAllTf32).  The last layer is computed TRANSPOSED (weights as the M operand) so
+// that its pooling epilogue reduces over time in registers.
 #include "gemm_tile.cuh"
 #include <cuda_bf16.h>
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ uint32_t decode_item(const StackParams& p, unsigned i
 // K loop of one tile on the MMA warp (leader CTA, warp-uniform; see tdnn_gemm.cu).
 template <bool kTf32>
 __device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* full_bar, uint64_t* empty_bar, uint32_t d, int kblocks, int& stage,
-                                         uint32_t& phase, uint32_t& rdy, unsigned long long& c_wait) {
+                                         uint32_t& phase, uint32_t& rdy, bool swap_ab, unsigned long long& c_wait) {
   constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
   for (int kb = 0; kb < kblocks; ++kb) {
     if (!(rdy & 1u)) {
@@ -107,8 +108,10 @@ __device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* full_bar, uint
     }
     tc_fence_after();
     const uint32_t a_addr = smem_u32(base + stage * STAGE_BYTES);
-    const uint64_t da = umma_desc_sw128(a_addr);
-    const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
+    // swap_ab: the weights are the M operand and the frames the N operand, i.e. the accumulator holds the TRANSPOSED tile
+    // (TMEM lane = channel, column = frame).  Both stage buffers are 128 rows x 128 bytes K-major, so it is only a swap.
+    const uint64_t da = umma_desc_sw128(swap_ab ? a_addr + A_BYTES : a_addr);
+    const uint64_t db = umma_desc_sw128(swap_ab ? a_addr : a_addr + A_BYTES);
     int stage_n = stage + 1;
     uint32_t phase_n = phase;
     if (stage_n == STACK_STAGES) { stage_n = 0; phase_n ^= 1u; }
@@ -244,8 +247,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         XVEC_CNT(c_tempty += clock64() - t0;)
         const uint32_t d = tmem_base + buf * BN;
         const int kblocks = L.taps * L.cpt;
-        if (kAllTf32 || L.tf32) mma_tile<true>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy, c_full);
-        else mma_tile<false>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy, c_full);
+        const bool pooled = static_cast<int>(item & 7u) == p.n_layers - 1;  // last layer: transposed accumulator (see the epilogue)
+        if (kAllTf32 || L.tf32) mma_tile<true>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy, pooled, c_full);
+        else mma_tile<false>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy, pooled, c_full);
         if (elect_one()) umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
         __syncwarp();
       }
@@ -315,7 +319,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
     const int cbeg = ((warp - 2) >> 2) * (BN / 2);  // this warp's half of the tile's columns
     const int cend = cbeg + BN / 2;
-    uint8_t* out_stage = epi_smem + (warp - 2) * (OUT_BUFS * OUT_BUF_BYTES);  // 2 x (32 rows x 128 bytes); also the pool transpose tile
+    uint8_t* out_stage = epi_smem + (warp - 2) * (OUT_BUFS * OUT_BUF_BYTES);  // 2 x (32 rows x 128 bytes)
     constexpr int OUT_ES = kAllTf32 ? 4 : 2;
     constexpr int GROUP_COLS = 128 / OUT_ES;         // columns per TMA-store box (128 bytes per row)
     constexpr int CHUNKS = GROUP_COLS / 32;          // tcgen05.ld chunks per box
@@ -360,66 +364,133 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       };
 
       if (layer == p.n_layers - 1) {
-        // last layer: statistics-pooling partials, nothing stored, nobody waits for this tile
-        if (lane == 0) tma_store_wait_read<0>();  // the transpose tile aliases the store staging boxes
-        __syncwarp();
-        const PoolArgs pa{p.rows, L.n, L.bias, p.row_utt, p.blk_slot_base, p.part};
-        pool_epilogue_tile(pa, tbase, row0, n0, cbeg, cend, reinterpret_cast<float*>(out_stage), lane, release_tmem);
+        // Last layer: statistics-pooling partials (replaces the reads of torch.mean / torch.std in stat_pool, main.py:59-63);
+        // nothing is stored and nobody waits for this tile.  The accumulator is TRANSPOSED (the MMA warp swapped the operands):
+        // TMEM lane = output channel, column = frame, so a thread holds 32 consecutive frames of ONE channel and the sums over
+        // time are plain register adds — no shared-memory transpose, no shuffles.  Per 32-frame block and utterance present in
+        // it: sum and sum of squares of r = relu(acc + bias) in the same pairwise order as pool_epilogue_tile (bit-identical).
+        const int ch = n0 + static_cast<int>(rank) * BN_CTA + q * 32 + lane;  // this thread's channel
+        const int ch_warp = ch - lane;
+        if (ch_warp < L.n) {  // warp-uniform: some of the warp's channels exist
+          const float bch = ch < L.n ? __ldg(L.bias + ch) : 0.f;
+          const float2 b2 = make_float2(bch, bch);
+          const int f0 = mt * BM + cbeg;  // first frame of this warp's 128 columns
+          int my_u[4], slot0[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // frame -> utterance of the four 32-frame blocks (lane = frame within the block)
+            const int f = f0 + 32 * k + lane;
+            my_u[k] = f < p.rows ? __ldg(p.row_utt + f) : -1;
+            slot0[k] = __ldg(p.blk_slot_base + ((f0 + 32 * k) >> 5));
+          }
+          const uint32_t tcol = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + cbeg;
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(tcol, va);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t(&v)[32] = (k & 1) ? vb : va;
+            if (k + 1 < 4) tmem_ld_32x32(tcol + 32 * (k + 1), (k & 1) ? va : vb);  // in flight while block k is reduced
+            unsigned remaining = __ballot_sync(0xffffffffu, my_u[k] >= 0);
+            int seg = 0;
+            while (remaining) {  // one pass per utterance present in this 32-frame block (warp-uniform)
+              const int lo = __ffs(remaining) - 1;
+              const int u = __shfl_sync(0xffffffffu, my_u[k], lo);
+              const unsigned m = __ballot_sync(0xffffffffu, my_u[k] == u);
+              float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+              if (m == 0xffffffffu) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), b2);
+                  a.x = fmaxf(a.x, 0.f);
+                  a.y = fmaxf(a.y, 0.f);
+                  s2 = __fadd2_rn(s2, a);
+                  q2 = __ffma2_rn(a, a, q2);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), b2);
+                  a.x = ((m >> j) & 1u) ? fmaxf(a.x, 0.f) : 0.f;
+                  a.y = ((m >> (j + 1)) & 1u) ? fmaxf(a.y, 0.f) : 0.f;
+                  s2 = __fadd2_rn(s2, a);
+                  q2 = __ffma2_rn(a, a, q2);
+                }
+              }
+              if (ch < L.n) {
+                float* dst = p.part + static_cast<size_t>(slot0[k] + seg) * 2 * L.n + ch;
+                dst[0] = s2.x + s2.y;
+                dst[L.n] = q2.x + q2.y;
+              }
+              remaining &= ~m;
+              ++seg;
+            }
+            if (k + 1 < 4) tmem_ld_wait();
+            if (k == 2) release_tmem();  // the last tcgen05.ld of the tile has landed
+          }
+        }
         if (!released) release_tmem();
         if (pend) flush();  // its stores were issued a whole tile ago
       } else {
         const CUtensorMap* my = &maps.y[layer];
-#pragma unroll 1
-        for (int bx = 0; bx < BOXES; ++bx) {
+        // tcgen05.ld of chunk k+1 is in flight while chunk k is converted and staged
+        constexpr int NCH = BOXES * CHUNKS;
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tbase + cbeg, va);
+        tmem_ld_wait();
+        uint8_t* ob = nullptr;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int bx = k / CHUNKS, cc = k % CHUNKS;
           const int c = cbeg + bx * GROUP_COLS;
-          uint8_t* ob = out_stage + (store_seq % OUT_BUFS) * OUT_BUF_BYTES;
-          if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();  // the store that last used this box has read it
-          __syncwarp();
+          uint32_t(&v)[32] = (k & 1) ? vb : va;
+          if (k + 1 < NCH) tmem_ld_32x32(tbase + cbeg + 32 * (k + 1), (k & 1) ? va : vb);
+          if (cc == 0) {
+            ob = out_stage + (store_seq % OUT_BUFS) * OUT_BUF_BYTES;
+            if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();  // the store that last used this box has read it
+            __syncwarp();
+          }
+          const int col0 = n0 + c + cc * 32;
+          // r = relu(acc + bias') — every BatchNorm is folded forward into the next layer's weights (xvector.py)
+          float o[32];
+          const float4* bp = reinterpret_cast<const float4*>(L.bias + col0);
 #pragma unroll
-          for (int cc = 0; cc < CHUNKS; ++cc) {
-            const int col0 = n0 + c + cc * 32;
-            uint32_t v[32];
-            tmem_ld_32x32(tbase + c + cc * 32, v);
-            tmem_ld_wait();
-            if (bx == BOXES - 1 && cc == CHUNKS - 1) release_tmem();
-            // r = relu(acc + bias') — every BatchNorm is folded forward into the next layer's weights (xvector.py)
-            float o[32];
-            const float4* bp = reinterpret_cast<const float4*>(L.bias + col0);
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 bb = __ldg(bp + (j4 >> 2));
+            const float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 0]), __uint_as_float(v[j4 + 1])), make_float2(bb.x, bb.y));
+            const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), make_float2(bb.z, bb.w));
+            o[j4 + 0] = a.x; o[j4 + 1] = a.y; o[j4 + 2] = d.x; o[j4 + 3] = d.y;
+          }
+          // row `lane` of the box, 16-byte pieces XOR-swizzled like CU_TENSOR_MAP_SWIZZLE_128B expects
+          uint8_t* orow = ob + lane * 128;
+          if constexpr (!kAllTf32) {
 #pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4) {
-              const float4 bb = __ldg(bp + (j4 >> 2));
-              const float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 0]), __uint_as_float(v[j4 + 1])), make_float2(bb.x, bb.y));
-              const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), make_float2(bb.z, bb.w));
-              o[j4 + 0] = a.x; o[j4 + 1] = a.y; o[j4 + 2] = d.x; o[j4 + 3] = d.y;
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              w.x = pack_bf16x2_relu(o[8 * j + 0], o[8 * j + 1]);
+              w.y = pack_bf16x2_relu(o[8 * j + 2], o[8 * j + 3]);
+              w.z = pack_bf16x2_relu(o[8 * j + 4], o[8 * j + 5]);
+              w.w = pack_bf16x2_relu(o[8 * j + 6], o[8 * j + 7]);
+              const int piece = cc * 4 + j;
+              *reinterpret_cast<uint4*>(orow + ((piece ^ (lane & 7)) << 4)) = w;
             }
-            // row `lane` of the box, 16-byte pieces XOR-swizzled like CU_TENSOR_MAP_SWIZZLE_128B expects
-            uint8_t* orow = ob + lane * 128;
-            if constexpr (!kAllTf32) {
+          } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 w;
-                w.x = pack_bf16x2_relu(o[8 * j + 0], o[8 * j + 1]);
-                w.y = pack_bf16x2_relu(o[8 * j + 2], o[8 * j + 3]);
-                w.z = pack_bf16x2_relu(o[8 * j + 4], o[8 * j + 5]);
-                w.w = pack_bf16x2_relu(o[8 * j + 6], o[8 * j + 7]);
-                const int piece = cc * 4 + j;
-                *reinterpret_cast<uint4*>(orow + ((piece ^ (lane & 7)) << 4)) = w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 w = make_float4(fmaxf(o[4 * j], 0.f), fmaxf(o[4 * j + 1], 0.f), fmaxf(o[4 * j + 2], 0.f), fmaxf(o[4 * j + 3], 0.f));
-                *reinterpret_cast<float4*>(orow + ((j ^ (lane & 7)) << 4)) = w;
-              }
+            for (int j = 0; j < 8; ++j) {
+              const float4 w = make_float4(fmaxf(o[4 * j], 0.f), fmaxf(o[4 * j + 1], 0.f), fmaxf(o[4 * j + 2], 0.f), fmaxf(o[4 * j + 3], 0.f));
+              *reinterpret_cast<float4*>(orow + ((j ^ (lane & 7)) << 4)) = w;
             }
           }
-          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          __syncwarp();
-          if (lane == 0) {
-            if (row0 < p.rows) tma_store_2d(my, ob, n0 + c, row0, p.pol_y);  // rows past the matrix are clipped
-            tma_store_commit();  // one group per box, also when nothing was stored, so that the group arithmetic below holds
+          if (k + 1 < NCH) tmem_ld_wait();
+          if (k == NCH - 2) release_tmem();  // the last tcgen05.ld of the tile has landed
+          if (cc == CHUNKS - 1) {
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+              if (row0 < p.rows) tma_store_2d(my, ob, n0 + c, row0, p.pol_y);  // rows past the matrix are clipped
+              tma_store_commit();  // one group per box, also when nothing was stored, so that the group arithmetic below holds
+            }
+            ++store_seq;
           }
-          ++store_seq;
         }
         if (pend) {  // the previous stored tile's groups are older than this tile's BOXES groups
           if (lane == 0 && !XVEC_SDBG(p, 2)) {
