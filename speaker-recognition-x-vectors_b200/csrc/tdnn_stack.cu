@@ -169,6 +169,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  XVEC_CNT(long long dbg_c0 = clock64(); unsigned long long dbg_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));)
 
   // Consumer side of the work-item ring: wait for entry `it`, read it, hand the slot back to the scheduler.
   auto ring_read = [&](int it) -> uint32_t {
@@ -508,6 +509,12 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  XVEC_CNT(if (blockIdx.x == 0 && threadIdx.x == 0) {  // SM clock during the launch: cycles (>>6) and nanoseconds of CTA 0
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    p.counter[8] = static_cast<unsigned>((clock64() - dbg_c0) >> 6);
+    p.counter[9] = static_cast<unsigned>(t1 - dbg_t0);
+  })
   cluster_sync_all();  // the peer may still be reading our smem / signalling our barriers until here
   if (warp == 1) {
     tc_fence_after();

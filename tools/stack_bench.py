@@ -55,6 +55,8 @@ for band in args.band.split(","):
         os.environ["XVEC_BAND"] = band
         os.environ["XVEC_STACK_DBG"] = dbg
         avg, best = run(args.iters)
-        cnt = sc.ctrl[:32].view(torch.int32).tolist()
+        cnt = sc.ctrl[:64].view(torch.int32).tolist()
         extra = ("  counters(spun,polls,fw,pub,mma_full,mma_tempty)=" + str([c for c in cnt[1:7]])) if any(cnt[1:7]) else ""
+        if cnt[9]:
+            extra += f" sm_clock={cnt[8] * 64 / cnt[9]:.3f} GHz cta0={cnt[9] / 1e3:.1f} us"
         print(f"band={band:>5} dbg={dbg}{extra} avg {avg * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {flops / avg / 1e9:7.1f} TFLOP/s", flush=True)
