@@ -32,6 +32,11 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    """Developer A/B builds: libxvec_b200_<name>.so with extra -D flags (select it with XVEC_LIB=...)."""
+    return _build_to(os.path.join(HERE, f"libxvec_b200_{name}.so"), list(NVCC_FLAGS) + [f"-D{d}" for d in defines], False, "_" + name)
+
+
 def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
     """debug=True builds libxvec_b200_debug.so with -DXVEC_DEBUG (per-tile clock stamps and epilogue/mainloop skip switches
     for tools/trace_tiles.py etc.; select it with XVEC_LIB=...)."""

@@ -261,14 +261,15 @@ __device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, u
   }
 }
 // One K step of the CTA-pair mainloop as a single instruction group, issued by a converged warp:
-//   - every lane first probes (try_wait, non-blocking) the barriers the NEXT step will need, so that the ~100+ cycle
-//     latency of the probe overlaps the MMA issue instead of sitting on the critical path of the issuing warp,
 //   - the elected lane issues the four tcgen05.mma of this 128-byte K chunk (32 bytes of K each) and the commits that
-//     release the operand stages.
+//     release the operand stages,
+//   - then every lane probes (try_wait) the barriers the NEXT step will need.  try_wait may suspend the thread until the
+//     phase completes or a system time limit expires, so it has to come AFTER the issue: in front of it, it delayed the
+//     MMAs of a stage that was ready until the following stage had landed (measured: 336 -> 3xx us for the stack kernel).
 // Returns bit0 = next A barrier already complete, bit1 = next B barrier already complete.
-// One producer step of the CTA-pair mainloop as a single instruction group (converged warp): probe the empty barrier of
-// the NEXT stage first (non-blocking; its latency overlaps the TMA issue), then the elected lane arms the leader's full
-// barrier (leader only) and issues the two tensor loads of this stage.  Returns 1 if the next stage was seen free.
+// One producer step of the CTA-pair mainloop as a single instruction group (converged warp): the elected lane arms the
+// leader's full barrier (leader only) and issues the two tensor loads of this stage, then the warp probes (try_wait, which may
+// suspend) the empty barrier of the NEXT stage.  Returns 1 if the next stage was seen free.
 __device__ __forceinline__ uint32_t tma_step_pair(uint32_t elected, uint32_t is_leader, uint32_t full_bar_local, uint32_t full_bar_leader,
                                                   uint32_t tx_bytes, uint32_t smem_a, const CUtensorMap* map_a, int32_t a0, int32_t a1,
                                                   uint64_t pol_a, uint32_t smem_b, const CUtensorMap* map_b, int32_t b0, int32_t b1,
@@ -280,16 +281,57 @@ __device__ __forceinline__ uint32_t tma_step_pair(uint32_t elected, uint32_t is_
       "setp.ne.b32 pe, %1, 0;\n\t"
       "setp.ne.b32 pl, %2, 0;\n\t"
       "and.pred pl, pl, pe;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 pw, [%15], %16;\n\t"
       "@pl mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %5;\n\t"
       "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%6], [%7, {%8, %9}], [%4], %10;\n\t"
       "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%11], [%12, {%13, %14}], [%4], %17;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 pw, [%15], %16;\n\t"
       "selp.u32 %0, 1, 0, pw;\n\t"
       "}"
       : "=r"(rdy)
       : "r"(elected), "r"(is_leader), "r"(full_bar_local), "r"(full_bar_leader), "r"(tx_bytes), "r"(smem_a),
         "l"(reinterpret_cast<uint64_t>(map_a)), "r"(a0), "r"(a1), "l"(pol_a), "r"(smem_b), "l"(reinterpret_cast<uint64_t>(map_b)),
         "r"(b0), "r"(b1), "r"(probe_bar), "r"(probe_par), "l"(pol_b)
+      : "memory");
+  return rdy;
+}
+
+// Producer step of the slab pipeline (tdnn_stack.cu) as one instruction group (converged warp): the elected lane arms the
+// leader's barriers and issues [the activation slab load of a new channel chunk, if do_a] + the weight-tile load of this
+// (chunk, tap); then the warp probes (try_wait, may suspend) the empty barrier of the next weight stage and, if probe_a, of
+// the next slab.  Returns bit0 = next slab seen free, bit1 = next weight stage seen free.
+__device__ __forceinline__ uint32_t tma_step_slab(uint32_t elected, uint32_t is_leader, uint32_t do_a, uint32_t fa_local, uint32_t fa_leader,
+                                                  uint32_t a_tx, uint32_t smem_a, const CUtensorMap* map_a, int32_t a0, int32_t a1,
+                                                  uint64_t pol_a, uint32_t fb_local, uint32_t fb_leader, uint32_t b_tx, uint32_t smem_b,
+                                                  const CUtensorMap* map_b, int32_t b0, int32_t b1, uint64_t pol_b, uint32_t probe_b_bar,
+                                                  uint32_t probe_b_par, uint32_t probe_a, uint32_t probe_a_bar, uint32_t probe_a_par) {
+  uint32_t rdy;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pl, pa, pla, ppa, pwa, pwb;\n\t"
+      ".reg .b32 ra, rb;\n\t"
+      "setp.ne.b32 pe, %1, 0;\n\t"
+      "setp.ne.b32 pl, %2, 0;\n\t"
+      "and.pred pl, pl, pe;\n\t"
+      "setp.ne.b32 pa, %3, 0;\n\t"
+      "and.pred pla, pa, pl;\n\t"
+      "and.pred pa, pa, pe;\n\t"
+      "setp.ne.b32 ppa, %22, 0;\n\t"
+      "setp.ne.b32 pwa, 0, 0;\n\t"
+      "@pla mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %6;\n\t"
+      "@pa cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%7], [%8, {%9, %10}], [%5], %11;\n\t"
+      "@pl mbarrier.arrive.expect_tx.shared::cta.b64 _, [%12], %14;\n\t"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%15], [%16, {%17, %18}], [%13], %19;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 pwb, [%20], %21;\n\t"
+      "@ppa mbarrier.try_wait.parity.shared::cta.b64 pwa, [%23], %24;\n\t"
+      "selp.u32 ra, 1, 0, pwa;\n\t"
+      "selp.u32 rb, 2, 0, pwb;\n\t"
+      "or.b32 %0, ra, rb;\n\t"
+      "}"
+      : "=r"(rdy)
+      : "r"(elected), "r"(is_leader), "r"(do_a), "r"(fa_local), "r"(fa_leader), "r"(a_tx), "r"(smem_a),
+        "l"(reinterpret_cast<uint64_t>(map_a)), "r"(a0), "r"(a1), "l"(pol_a), "r"(fb_local), "r"(fb_leader), "r"(b_tx), "r"(smem_b),
+        "l"(reinterpret_cast<uint64_t>(map_b)), "r"(b0), "r"(b1), "l"(pol_b), "r"(probe_b_bar), "r"(probe_b_par), "r"(probe_a),
+        "r"(probe_a_bar), "r"(probe_a_par)
       : "memory");
   return rdy;
 }
@@ -316,8 +358,6 @@ __device__ __forceinline__ uint32_t umma_step_pair(uint32_t elected, uint32_t tm
       "and.b32 f, %7, 8;\n\tsetp.ne.b32 ppb, f, 0;\n\t"                                                          \
       "setp.ne.b32 pwa, 0, 0;\n\t"                                                                                \
       "setp.ne.b32 pwb, 0, 0;\n\t"                                                                                \
-      "@ppa mbarrier.try_wait.parity.shared::cta.b64 pwa, [%10], %11;\n\t"                                        \
-      "@ppb mbarrier.try_wait.parity.shared::cta.b64 pwb, [%12], %13;\n\t"                                        \
       "add.u64 a1, %3, 2;\n\tadd.u64 a2, %3, 4;\n\tadd.u64 a3, %3, 6;\n\t"                                      \
       "add.u64 b1, %4, 2;\n\tadd.u64 b2, %4, 4;\n\tadd.u64 b3, %4, 6;\n\t"                                      \
       "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%2], %3, %4, %5, pacc;\n\t"                                   \
@@ -328,6 +368,8 @@ __device__ __forceinline__ uint32_t umma_step_pair(uint32_t elected, uint32_t tm
       "and.b32 f, %7, 1;\n\tsetp.ne.b32 pca, f, 0;\n\tand.pred pca, pca, pe;\n\t"                               \
       "@pcb tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], mk;\n\t" \
       "@pca tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], mk;\n\t" \
+      "@ppa mbarrier.try_wait.parity.shared::cta.b64 pwa, [%10], %11;\n\t"                                        \
+      "@ppb mbarrier.try_wait.parity.shared::cta.b64 pwb, [%12], %13;\n\t"                                        \
       "selp.u32 ra, 1, 0, pwa;\n\t"                                                                               \
       "selp.u32 rb, 2, 0, pwb;\n\t"                                                                               \
       "or.b32 %0, ra, rb;\n\t"                                                                                    \

@@ -142,8 +142,8 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (tt % p.n_tiles) * BN + static_cast<int>(rank) * BN_CTA;
       const int kb0 = ks * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
-        const int tap = kb / p.cpt;
-        const int ch = kb - tap * p.cpt;
+        const int ch = kb / p.taps;  // channel chunk outermost, taps innermost: the K order of tdnn_stack.cu (bit-identical sums)
+        const int tap = kb - ch * p.taps;
         if (!rdy) mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
         if (kb == kb0 && lane == 0) trace(p, pit, 0);
         const int arow = m0 + tap_off_s[tap];
@@ -163,7 +163,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           continue;
         }
         rdy = tma_step_pair(elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, smem_u32(&full_bar[stage]), lf, 2 * STAGE_BYTES, sa, &tmA,
-                            ch * BKE, arow, p.pol_a, sa + A_BYTES, &tmB, kb * BKE, n0, p.pol_b, smem_u32(&empty_bar[stage_n]),
+                            ch * BKE, arow, p.pol_a, sa + A_BYTES, &tmB, (tap * p.cpt + ch) * BKE, n0, p.pol_b, smem_u32(&empty_bar[stage_n]),
                             phase_n ^ 1u);
         stage = stage_n;
         phase = phase_n;

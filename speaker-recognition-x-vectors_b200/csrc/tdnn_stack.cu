@@ -27,7 +27,25 @@
 
 namespace xvec {
 
-constexpr int STACK_STAGES = 5;
+// Operand staging: the activation ("A") side is loaded once per 128-byte channel chunk as a SLAB of 128 + max_tap_offset frame
+// rows and reused by every tap of the layer — tap j's MMA reads the slab through a descriptor whose start address is shifted
+// by tap_off[j] rows (the 128-byte swizzle is a function of the absolute shared-memory address, so a row shift keeps TMA's
+// and UMMA's patterns in step as long as the slab base is 1024-byte aligned).  The weight ("B") side streams one 128 x 128-byte
+// tile per (chunk, tap).  The kernel is bound by the L2 -> SM operand traffic (measured: the MMA warp waits ~350 of every ~650
+// cycles per K chunk for operands), and slabs cut it from 32 KiB to 16 + 17/taps KiB per K chunk.
+// Ring depths, measured on B200 (256 x 300 frames, bf16; slabs / weight stages / store staging boxes per epilogue warp):
+// 4/5/2 316 us, 5/4/2 333 us, 6/5/1 308 us, 5/6/1 302 us — operand bytes in flight matter more than a second staging box.
+#ifndef XVEC_A_SLABS
+#define XVEC_A_SLABS 5
+#define XVEC_B_STAGES 6
+#define XVEC_STACK_OUT_BUFS 1
+#endif
+constexpr int A_SLABS = XVEC_A_SLABS;
+constexpr int B_STAGES = XVEC_B_STAGES;
+constexpr int STACK_OUT_BUFS = XVEC_STACK_OUT_BUFS;  // store staging boxes (32 rows x 128 bytes) per epilogue warp
+constexpr int SLAB_ROWS_MAX = BM_CTA + 8;             // frame rows per slab (128 + the largest tap offset, <= 8)
+constexpr int SLAB_BYTES = SLAB_ROWS_MAX * BK_BYTES;  // 17 KiB, a multiple of 1024
+static_assert(SLAB_BYTES % 1024 == 0, "slab bases must stay 1024-byte aligned for SWIZZLE_128B");
 constexpr int SCHED_SLOTS = 8;            // work-item ring between the scheduler and the warp roles
 constexpr uint32_t ITEM_DONE = 0xFFFFFFFFu;
 constexpr int SCHED_CONSUMERS = 2 * EPI_WARPS + 4;  // per slot: both producers, leader MMA warp, peer dependency warp, 8 epilogue warps of each CTA
@@ -37,6 +55,7 @@ constexpr int STACK_THREADS = GEMM_THREADS + 32;
 struct StackLayer {
   int n, n_tiles, taps, cpt;  // K loop = taps * cpt chunks of 128 bytes
   int tf32;                   // operand kind of this layer (1: float32 activations / TF32 math, 0: bf16)
+  int slab_rows;              // 128 + largest tap offset: frame rows one activation slab holds (= the A tensor map's box)
   int tap_off[XVEC_MAX_TAPS];
   const float* bias;
 };
@@ -95,47 +114,73 @@ __device__ __forceinline__ uint32_t decode_item(const StackParams& p, unsigned i
 #define XVEC_CNT(...)
 #endif
 
-// K loop of one tile on the MMA warp (leader CTA, warp-uniform; see tdnn_gemm.cu).
+// K loop of one tile on the MMA warp (leader CTA, warp-uniform; see tdnn_gemm.cu): for every channel chunk one activation slab,
+// for every tap one weight tile; the slab goes back to the producer with the last tap's commit.
+struct MmaRing {
+  int slab = 0, bst = 0;
+  uint32_t aph = 0, bph = 0, rdy = 0;  // rdy: bit0 next slab seen full, bit1 next weight tile seen full
+};
 template <bool kTf32>
-__device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* full_bar, uint64_t* empty_bar, uint32_t d, int kblocks, int& stage,
-                                         uint32_t& phase, uint32_t& rdy, bool swap_ab, unsigned long long& c_wait) {
+__device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* fa, uint64_t* ea, uint64_t* fb, uint64_t* eb, uint32_t d, const StackLayer& L,
+                                         MmaRing& r, bool swap_ab, unsigned long long& c_wait, unsigned long long& c_step) {
   constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
-  for (int kb = 0; kb < kblocks; ++kb) {
-    if (!(rdy & 1u)) {
+  uint32_t acc = 0;
+  for (int ch = 0; ch < L.cpt; ++ch) {
+    if (!(r.rdy & 1u)) {
       XVEC_CNT(const long long t0 = clock64();)
-      mbar_wait(&full_bar[stage], phase, 3);
+      mbar_wait(&fa[r.slab], r.aph, 3);
       XVEC_CNT(c_wait += clock64() - t0;)
     }
-    tc_fence_after();
-    const uint32_t a_addr = smem_u32(base + stage * STAGE_BYTES);
-    // swap_ab: the weights are the M operand and the frames the N operand, i.e. the accumulator holds the TRANSPOSED tile
-    // (TMEM lane = channel, column = frame).  Both stage buffers are 128 rows x 128 bytes K-major, so it is only a swap.
-    const uint64_t da = umma_desc_sw128(swap_ab ? a_addr + A_BYTES : a_addr);
-    const uint64_t db = umma_desc_sw128(swap_ab ? a_addr : a_addr + A_BYTES);
-    int stage_n = stage + 1;
-    uint32_t phase_n = phase;
-    if (stage_n == STACK_STAGES) { stage_n = 0; phase_n ^= 1u; }
-    rdy = umma_step_pair<kTf32>(elect_one() ? 1u : 0u, d, da, db, idesc, kb > 0 ? 1u : 0u, STEP_COMMIT_A | STEP_PROBE_A,
-                                smem_u32(&empty_bar[stage]), 0u, smem_u32(&full_bar[stage_n]), phase_n, 0u, 0u);
-    stage = stage_n;
-    phase = phase_n;
+    r.rdy &= ~1u;  // bit0 is set again by the last tap's probe of the NEXT slab
+    int slab_n = r.slab + 1;
+    uint32_t aph_n = r.aph;
+    if (slab_n == A_SLABS) { slab_n = 0; aph_n ^= 1u; }
+    const uint32_t slab_addr = smem_u32(base + r.slab * SLAB_BYTES);
+    for (int tap = 0; tap < L.taps; ++tap) {
+      if (!(r.rdy & 2u)) {
+        XVEC_CNT(const long long t0 = clock64();)
+        mbar_wait(&fb[r.bst], r.bph, 3);
+        XVEC_CNT(c_wait += clock64() - t0;)
+      }
+      tc_fence_after();
+      const uint32_t x_addr = slab_addr + static_cast<uint32_t>(L.tap_off[tap]) * BK_BYTES;  // the slab, shifted by the tap's rows
+      const uint32_t w_addr = smem_u32(base + A_SLABS * SLAB_BYTES + r.bst * B_BYTES);
+      // swap_ab: the weights are the M operand and the frames the N operand, i.e. the accumulator holds the TRANSPOSED tile
+      // (TMEM lane = channel, column = frame).  Both operands are 128 rows x 128 bytes K-major, so it is only a swap.
+      const uint64_t da = umma_desc_sw128(swap_ab ? w_addr : x_addr);
+      const uint64_t db = umma_desc_sw128(swap_ab ? x_addr : w_addr);
+      int bst_n = r.bst + 1;
+      uint32_t bph_n = r.bph;
+      if (bst_n == B_STAGES) { bst_n = 0; bph_n ^= 1u; }
+      const bool last_tap = tap == L.taps - 1;
+      const uint32_t flags = STEP_COMMIT_B | STEP_PROBE_B | (last_tap ? (STEP_COMMIT_A | STEP_PROBE_A) : 0u);
+      XVEC_CNT(const long long ts = clock64();)
+      const uint32_t got = umma_step_pair<kTf32>(elect_one() ? 1u : 0u, d, da, db, idesc, acc, flags, smem_u32(&ea[r.slab]),
+                                                 smem_u32(&eb[r.bst]), smem_u32(&fa[slab_n]), aph_n, smem_u32(&fb[bst_n]), bph_n);
+      XVEC_CNT(c_step += clock64() - ts;)
+      r.rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
+      acc = 1u;
+      r.bst = bst_n;
+      r.bph = bph_n;
+    }
+    r.slab = slab_n;
+    r.aph = aph_n;
   }
 }
 
-constexpr int stack_smem_bytes() { return 1024 + STACK_STAGES * STAGE_BYTES + EPI_WARPS * OUT_BUFS * OUT_BUF_BYTES; }
+constexpr int stack_smem_bytes() { return 1024 + A_SLABS * SLAB_BYTES + B_STAGES * B_BYTES + EPI_WARPS * STACK_OUT_BUFS * OUT_BUF_BYTES; }
 
 template <bool kAllTf32>
 __global__ void __launch_bounds__(STACK_THREADS, 1)
 tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant__ StackParams p) {
-  constexpr int STAGES = STACK_STAGES;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t fa_bar[A_SLABS], ea_bar[A_SLABS], fb_bar[B_STAGES], eb_bar[B_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint64_t sfull_bar[SCHED_SLOTS], sempty_bar[SCHED_SLOTS], dep_bar[SCHED_SLOTS], credit_bar;
   __shared__ uint32_t sched_item[SCHED_SLOTS];
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte alignment
-  uint8_t* epi_smem = base + STAGES * STAGE_BYTES;
+  uint8_t* epi_smem = base + A_SLABS * SLAB_BYTES + B_STAGES * B_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -147,9 +192,13 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       tma_prefetch_desc(&maps.b[l]);
       if (l + 1 < p.n_layers) tma_prefetch_desc(&maps.y[l]);
     }
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx (bytes of both CTAs)
-      mbar_init(&empty_bar[s], 1);  // leader's multicast commit
+    for (int s = 0; s < A_SLABS; ++s) {
+      mbar_init(&fa_bar[s], 1);  // leader's arrive.expect_tx (bytes of both CTAs)
+      mbar_init(&ea_bar[s], 1);  // leader's multicast commit (last tap of the chunk)
+    }
+    for (int s = 0; s < B_STAGES; ++s) {
+      mbar_init(&fb_bar[s], 1);
+      mbar_init(&eb_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);               // leader's multicast commit
@@ -187,11 +236,8 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     // Per tile: read the work item (published by the scheduler warp while the previous tile was loading), check that this
     // CTA's dependency warp has resolved its inputs, tell the scheduler that the tile has started, then run the K loop.
-    int stage = 0;
-    uint32_t phase = 0, rdy = 0;
-    uint32_t leader_full[STAGES];
-#pragma unroll
-    for (int i = 0; i < STAGES; ++i) leader_full[i] = mapa_u32(smem_u32(&full_bar[i]), 0);
+    int slab = 0, bst = 0;
+    uint32_t aph = 0, bph = 0, rdy = 0;  // rdy: bit0 next slab seen free, bit1 next weight stage seen free
     XVEC_CNT(unsigned long long c_fw = 0, c_pub = 0;)
     for (int it = 0;; ++it) {
       XVEC_CNT(long long t0 = clock64();)
@@ -208,23 +254,31 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       const int n0 = nt * BN + static_cast<int>(rank) * BN_CTA;
       const CUtensorMap* ma = &maps.a[layer];
       const CUtensorMap* mb = &maps.b[layer];
-      const int kblocks = L.taps * L.cpt;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int tap = kb / L.cpt;
-        const int ch = kb - tap * L.cpt;
-        if (!rdy) mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-        const int arow = m0 + L.tap_off[tap];
-        int stage_n = stage + 1;
-        uint32_t phase_n = phase;
-        if (stage_n == STAGES) { stage_n = 0; phase_n ^= 1u; }
-        uint32_t lf = leader_full[0];
-#pragma unroll
-        for (int i = 1; i < STAGES; ++i) lf = (stage == i) ? leader_full[i] : lf;
-        const uint32_t sa = smem_u32(base + stage * STAGE_BYTES);
-        rdy = tma_step_pair(elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, smem_u32(&full_bar[stage]), lf, 2 * STAGE_BYTES, sa, ma, ch * bke,
-                            arow, p.pol_a, sa + A_BYTES, mb, kb * bke, n0, p.pol_b, smem_u32(&empty_bar[stage_n]), phase_n ^ 1u);
-        stage = stage_n;
-        phase = phase_n;
+      const uint32_t slab_tx = 2u * static_cast<uint32_t>(L.slab_rows) * BK_BYTES;  // bytes of both CTAs' slabs
+      for (int ch = 0; ch < L.cpt; ++ch) {
+        if (!(rdy & 1u)) mbar_wait(&ea_bar[slab], aph ^ 1u, 1);
+        int slab_n = slab + 1;
+        uint32_t aph_n = aph;
+        if (slab_n == A_SLABS) { slab_n = 0; aph_n ^= 1u; }
+        rdy &= ~1u;
+        for (int tap = 0; tap < L.taps; ++tap) {
+          if (!(rdy & 2u)) mbar_wait(&eb_bar[bst], bph ^ 1u, 1);
+          int bst_n = bst + 1;
+          uint32_t bph_n = bph;
+          if (bst_n == B_STAGES) { bst_n = 0; bph_n ^= 1u; }
+          const bool last_tap = tap == L.taps - 1;
+          const uint32_t got = tma_step_slab(
+              elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, tap == 0 ? 1u : 0u, smem_u32(&fa_bar[slab]), mapa_u32(smem_u32(&fa_bar[slab]), 0),
+              slab_tx, smem_u32(base + slab * SLAB_BYTES), ma, ch * bke, m0, p.pol_a, smem_u32(&fb_bar[bst]),
+              mapa_u32(smem_u32(&fb_bar[bst]), 0), 2u * B_BYTES, smem_u32(base + A_SLABS * SLAB_BYTES + bst * B_BYTES), mb,
+              (tap * L.cpt + ch) * bke, n0, p.pol_b, smem_u32(&eb_bar[bst_n]), bph_n ^ 1u, last_tap ? 1u : 0u, smem_u32(&ea_bar[slab_n]),
+              aph_n ^ 1u);
+          rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
+          bst = bst_n;
+          bph = bph_n;
+        }
+        slab = slab_n;
+        aph = aph_n;
       }
     }
     XVEC_CNT(if (lane == 0) {
@@ -234,29 +288,32 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (rank == 0) {
-      int stage = 0;
-      uint32_t phase = 0, rdy = 0;
-      unsigned long long c_full = 0, c_tempty = 0;
+      MmaRing ring;
+      unsigned long long c_full = 0, c_tempty = 0, c_step = 0, c_ring = 0;
       for (int it = 0;; ++it) {
+        XVEC_CNT(const long long tr = clock64();)
         const uint32_t item = ring_read(it);
+        XVEC_CNT(c_ring += clock64() - tr;)
         if (item == ITEM_DONE) break;
         const StackLayer& L = p.L[item & 7u];
         const int buf = it & 1;
         const uint32_t use = (it >> 1) & 1;
         XVEC_CNT(const long long t0 = clock64();)
         mbar_wait(&tempty_bar[buf], use ^ 1u, 2);  // both CTAs' epilogues have drained this accumulator buffer
-        XVEC_CNT(c_tempty += clock64() - t0;)
+        XVEC_CNT(c_tempty += clock64() - t0; const int dl = item & 7u; if (lane == 0) atomicAdd(p.counter + 16 + dl, static_cast<unsigned>((clock64() - t0) >> 4));)
         const uint32_t d = tmem_base + buf * BN;
-        const int kblocks = L.taps * L.cpt;
         const bool pooled = static_cast<int>(item & 7u) == p.n_layers - 1;  // last layer: transposed accumulator (see the epilogue)
-        if (kAllTf32 || L.tf32) mma_tile<true>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy, pooled, c_full);
-        else mma_tile<false>(base, full_bar, empty_bar, d, kblocks, stage, phase, rdy, pooled, c_full);
+        if (kAllTf32 || L.tf32) mma_tile<true>(base, fa_bar, ea_bar, fb_bar, eb_bar, d, L, ring, pooled, c_full, c_step);
+        else mma_tile<false>(base, fa_bar, ea_bar, fb_bar, eb_bar, d, L, ring, pooled, c_full, c_step);
         if (elect_one()) umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
         __syncwarp();
+        XVEC_CNT(if (lane == 0) atomicAdd(p.counter + 24 + (item & 7u), static_cast<unsigned>((clock64() - tr) >> 4));)
       }
       XVEC_CNT(if (lane == 0) {
         atomicAdd(p.counter + 5, static_cast<unsigned>(c_full >> 6));
         atomicAdd(p.counter + 6, static_cast<unsigned>(c_tempty >> 6));
+        atomicAdd(p.counter + 10, static_cast<unsigned>(c_step >> 6));
+        atomicAdd(p.counter + 11, static_cast<unsigned>(c_ring >> 6));
       })
     }
   } else if (warp == DEP_WARP) {
@@ -320,7 +377,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
     const int cbeg = ((warp - 2) >> 2) * (BN / 2);  // this warp's half of the tile's columns
     const int cend = cbeg + BN / 2;
-    uint8_t* out_stage = epi_smem + (warp - 2) * (OUT_BUFS * OUT_BUF_BYTES);  // 2 x (32 rows x 128 bytes)
+    uint8_t* out_stage = epi_smem + (warp - 2) * (STACK_OUT_BUFS * OUT_BUF_BYTES);
     constexpr int OUT_ES = kAllTf32 ? 4 : 2;
     constexpr int GROUP_COLS = 128 / OUT_ES;         // columns per TMA-store box (128 bytes per row)
     constexpr int CHUNKS = GROUP_COLS / 32;          // tcgen05.ld chunks per box
@@ -446,8 +503,8 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
           uint32_t(&v)[32] = (k & 1) ? vb : va;
           if (k + 1 < NCH) tmem_ld_32x32(tbase + cbeg + 32 * (k + 1), (k & 1) ? va : vb);
           if (cc == 0) {
-            ob = out_stage + (store_seq % OUT_BUFS) * OUT_BUF_BYTES;
-            if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();  // the store that last used this box has read it
+            ob = out_stage + (store_seq % STACK_OUT_BUFS) * OUT_BUF_BYTES;
+            if (lane == 0) tma_store_wait_read<STACK_OUT_BUFS - 1>();  // the store that last used this box has read it
             __syncwarp();
           }
           const int col0 = n0 + c + cc * 32;
@@ -583,7 +640,7 @@ bool stack_supported(const XvecLayerDesc* tdnn, int n_tdnn, int64_t rows) {
       if (tdnn[i].tap_offsets[j] < 0) return false;
       if (tdnn[i].tap_offsets[j] > max_off) max_off = tdnn[i].tap_offsets[j];
     }
-    if (max_off > BM_CTA) return false;  // a tile reads its own m-tile and the first rows of the next one only
+    if (max_off > SLAB_ROWS_MAX - BM_CTA) return false;  // one activation slab holds 128 + max_off <= 136 frame rows
   }
   return true;
 }
@@ -618,12 +675,17 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const float* x, int64_
     L.taps = d.taps;
     L.cpt = (d.cin + bke - 1) / bke;
     L.tf32 = d.dtype == XVEC_F32 ? 1 : 0;
-    for (int j = 0; j < d.taps; ++j) L.tap_off[j] = d.tap_offsets[j];
+    int max_off = 0;
+    for (int j = 0; j < d.taps; ++j) {
+      L.tap_off[j] = d.tap_offsets[j];
+      if (d.tap_offsets[j] > max_off) max_off = d.tap_offsets[j];
+    }
+    L.slab_rows = BM_CTA + max_off;
     L.bias = d.bias_dev;
     if (reinterpret_cast<uintptr_t>(d.bias_dev) & 15u) return set_error(XVEC_E_ARG, "bias must be 16-byte aligned");
     items_per_mtile += L.n_tiles;
     rc = make_tmap_2d(&local_maps.a[l], h, h_dtype, static_cast<uint64_t>(d.cin), static_cast<uint64_t>(rows), static_cast<uint64_t>(h_ld),
-                      bke, BM_CTA);
+                      bke, static_cast<uint32_t>(L.slab_rows));
     if (rc) return rc;
     const uint64_t kpad = static_cast<uint64_t>(d.taps) * L.cpt * bke;
     rc = make_tmap_2d(&local_maps.b[l], d.w_packed_dev, d.dtype, kpad, static_cast<uint64_t>(L.n_tiles) * BN, kpad, bke, BN_CTA);
