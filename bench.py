@@ -165,7 +165,7 @@ def run_b200(args, rank, world, local_rank):
         x_dev[i].copy_(x_host[i % n_batches])
         x_dev[i].mul_(1.0 + 0.01 * (i // n_batches))
     lengths = [FRAMES] * BATCH
-    n_inflight = 2  # batches in flight on separate streams: the tail wave of one kernel overlaps the next batch's kernels
+    n_inflight = int(os.environ.get("XVEC_BENCH_INFLIGHT", "2"))  # batches in flight on separate streams: the tail of one batch overlaps the next batch's kernels
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_inflight)]
 
     def step(i):

@@ -69,7 +69,9 @@ XVEC_API int64_t xvec_packed_n(int n);
 /* Pack a Linear weight for xvec_tdnn_layer.
  * replaces: the layout nn.Linear(input_size*len(context), output_size) stores (tdnn_layer.py:19): W (n, taps*cin)
  * row-major, column index = tap*cin + channel (context-major, because of torch.cat(..., 2) at tdnn_layer.py:29).
- * w_dev: float32 (n, taps*cin).  out_dev: (xvec_packed_n(n), xvec_packed_k(cin,taps,dtype)) of `dtype`, zero padded. */
+ * w_dev: float32 (n, taps*cin).  out_dev: xvec_packed_n(n) * xvec_packed_k(cin,taps,dtype) elements of `dtype`, zero padded,
+ * stored K-chunk-major ([128-byte K chunk][row][element]: every 128-row x 128-byte TMA box is one contiguous 16 KiB run);
+ * the layout is private to this library — treat the buffer as opaque. */
 XVEC_API int xvec_pack_weight(const float* w_dev, int n, int taps, int cin, int dtype, void* out_dev, void* stream);
 
 /* One TDNN layer on the flat frame matrix, no unfold in memory:

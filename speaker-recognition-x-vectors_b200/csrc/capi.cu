@@ -162,11 +162,18 @@ int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const float* x_d
                        nullptr, 1, nullptr, XVEC_F32, 0, row_utt_dev, blk_slot_base_dev, part_dev, rows, true, nullptr, 0, stream);
     if (rc) return rc;
   }
+#ifdef XVEC_DEBUG
+  static const int skip_tail = getenv("XVEC_SKIP_TAIL") ? atoi(getenv("XVEC_SKIP_TAIL")) : 0;  // experiment: 1 = no segment layers, 2 = no finalize either
+  if (skip_tail >= 2) return XVEC_OK;
+#endif
   const int fc_in_dtype = fc[0].dtype;
   if (fc_in_dtype == XVEC_BF16 && !pooled_lp_dev) return set_error(XVEC_E_ARG, "pooled_lp_dev is required for bf16 segment layers");
   rc = xvec_pool_finalize(part_dev, utt_slot_start_dev, n_pool_dev, n_utts, last.n, bn_last_scale_dev, bn_last_shift_dev, pooled_dev,
                           fc_in_dtype == XVEC_BF16 ? pooled_lp_dev : nullptr, XVEC_BF16, 2 * static_cast<int64_t>(last.n), stream);
   if (rc) return rc;
+#ifdef XVEC_DEBUG
+  if (skip_tail >= 1) return XVEC_OK;
+#endif
   const void* a = fc_in_dtype == XVEC_BF16 ? pooled_lp_dev : static_cast<const void*>(pooled_dev);
   int64_t a_ld = 2 * static_cast<int64_t>(last.n);
   for (int i = 0; i < n_fc; ++i) {

@@ -181,10 +181,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int n, int taps,
     const int tap = kk / tap_k;
     const int ch = kk - tap * tap_k;
     const float v = (row < n && ch < cin) ? w[row * (static_cast<long long>(taps) * cin) + tap * cin + ch] : 0.f;
+    // chunk-major: [K chunk of 128 bytes][row][element in chunk] — the 128-row x 128-byte box the GEMM producers load per
+    // K chunk is then one contiguous 16 KiB run of global memory instead of 128 pieces k_pad*elsize bytes apart
+    const int bke = dtype == XVEC_BF16 ? 64 : 32;
+    const long long o = (static_cast<long long>(kk / bke) * n_pad + row) * bke + kk % bke;
     if (dtype == XVEC_BF16)
-      reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+      reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(v);
     else
-      reinterpret_cast<float*>(out)[i] = v;
+      reinterpret_cast<float*>(out)[o] = v;
   }
 }
 

@@ -163,7 +163,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           continue;
         }
         rdy = tma_step_pair(elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, smem_u32(&full_bar[stage]), lf, 2 * STAGE_BYTES, sa, &tmA,
-                            ch * BKE, arow, p.pol_a, sa + A_BYTES, &tmB, (tap * p.cpt + ch) * BKE, n0, p.pol_b, smem_u32(&empty_bar[stage_n]),
+                            ch * BKE, arow, p.pol_a, sa + A_BYTES, &tmB, 0, (tap * p.cpt + ch) * (p.n_tiles * BN) + n0, p.pol_b, smem_u32(&empty_bar[stage_n]),
                             phase_n ^ 1u);
         stage = stage_n;
         phase = phase_n;
@@ -541,8 +541,8 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
   CUtensorMap ta, tb, ty;
   rc = make_tmap_2d(&ta, x, x_dtype, static_cast<uint64_t>(cin), static_cast<uint64_t>(x_rows), static_cast<uint64_t>(x_ld), bke, BM_CTA);
   if (rc) return rc;
-  const uint64_t kpad = static_cast<uint64_t>(taps) * p.cpt * bke;
-  rc = make_tmap_2d(&tb, w_packed, x_dtype, kpad, static_cast<uint64_t>(p.n_tiles) * BN, kpad, bke, BN_CTA);
+  // packed weights are chunk-major (xvec_pack_weight): a (kblocks * n_pad) x bke matrix, one contiguous 16 KiB box per load
+  rc = make_tmap_2d(&tb, w_packed, x_dtype, bke, static_cast<uint64_t>(taps) * p.cpt * p.n_tiles * BN, bke, bke, BN_CTA);
   if (rc) return rc;
   if (p.vec_store) {
     const uint64_t yrows = split ? static_cast<uint64_t>(p.ksplit) * p.rows_pad : static_cast<uint64_t>(rows);

@@ -56,6 +56,7 @@ struct StackLayer {
   int n, n_tiles, taps, cpt;  // K loop = taps * cpt chunks of 128 bytes
   int tf32;                   // operand kind of this layer (1: float32 activations / TF32 math, 0: bf16)
   int slab_rows;              // 128 + largest tap offset: frame rows one activation slab holds (= the A tensor map's box)
+  int n_pad;                  // rows of one K chunk of the chunk-major packed weights (n_tiles * 256)
   int tap_off[XVEC_MAX_TAPS];
   const float* bias;
 };
@@ -271,7 +272,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
               elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, tap == 0 ? 1u : 0u, smem_u32(&fa_bar[slab]), mapa_u32(smem_u32(&fa_bar[slab]), 0),
               slab_tx, smem_u32(base + slab * SLAB_BYTES), ma, ch * bke, m0, p.pol_a, smem_u32(&fb_bar[bst]),
               mapa_u32(smem_u32(&fb_bar[bst]), 0), 2u * B_BYTES, smem_u32(base + A_SLABS * SLAB_BYTES + bst * B_BYTES), mb,
-              (tap * L.cpt + ch) * bke, n0, p.pol_b, smem_u32(&eb_bar[bst_n]), bph_n ^ 1u, last_tap ? 1u : 0u, smem_u32(&ea_bar[slab_n]),
+              0, (tap * L.cpt + ch) * L.n_pad + n0, p.pol_b, smem_u32(&eb_bar[bst_n]), bph_n ^ 1u, last_tap ? 1u : 0u, smem_u32(&ea_bar[slab_n]),
               aph_n ^ 1u);
           rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
           bst = bst_n;
@@ -687,8 +688,10 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const float* x, int64_
     rc = make_tmap_2d(&local_maps.a[l], h, h_dtype, static_cast<uint64_t>(d.cin), static_cast<uint64_t>(rows), static_cast<uint64_t>(h_ld),
                       bke, static_cast<uint32_t>(L.slab_rows));
     if (rc) return rc;
-    const uint64_t kpad = static_cast<uint64_t>(d.taps) * L.cpt * bke;
-    rc = make_tmap_2d(&local_maps.b[l], d.w_packed_dev, d.dtype, kpad, static_cast<uint64_t>(L.n_tiles) * BN, kpad, bke, BN_CTA);
+    // packed weights are chunk-major (xvec_pack_weight): a (kblocks * n_pad) x bke matrix, one contiguous 16 KiB box per load
+    const uint64_t n_pad = static_cast<uint64_t>(L.n_tiles) * BN;
+    L.n_pad = static_cast<int>(n_pad);
+    rc = make_tmap_2d(&local_maps.b[l], d.w_packed_dev, d.dtype, bke, static_cast<uint64_t>(d.taps) * L.cpt * n_pad, bke, bke, BN_CTA);
     if (rc) return rc;
     if (l + 1 < n_tdnn) {
       rc = make_tmap_2d(&local_maps.y[l], act[l & 1], act_dtype, static_cast<uint64_t>(d.n), static_cast<uint64_t>(rows),
@@ -733,7 +736,13 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const float* x, int64_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(ctrl, 0, static_cast<size_t>(stack_ctrl_bytes(rows, n_tdnn)), st);
   if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaMemsetAsync(ctrl): %s", cudaGetErrorString(e));
-  const int64_t pairs = static_cast<int64_t>(acc) < max_pairs ? acc : max_pairs;
+  int64_t pairs = static_cast<int64_t>(acc) < max_pairs ? acc : max_pairs;
+#ifdef XVEC_DEBUG
+  if (const char* e = getenv("XVEC_STACK_PAIRS")) {  // experiment: fewer CTA pairs (is the operand stream a per-SM or a global limit?)
+    const int v = atoi(e);
+    if (v > 0 && v < pairs) pairs = v;
+  }
+#endif
   const int grid = 2 * static_cast<int>(pairs);
   return all_tf32 ? launch_stack<true>(local_maps, p, grid, st) : launch_stack<false>(local_maps, p, grid, st);
 }
