@@ -45,7 +45,7 @@ extern "C" {
 
 #define XVEC_MAX_TAPS 8
 #define XVEC_TILE_N 256     /* output-channel tile; packed weights are padded to a multiple of this many rows */
-#define XVEC_POOL_BLOCK 32  /* rows per pooling partial block of the fused TDNN5+pool epilogue */
+#define XVEC_POOL_BLOCK 128 /* rows per pooling partial block of the fused TDNN5+pool epilogue */
 #define XVEC_POOL_CHUNK 128 /* rows per partial of the standalone statistics-pooling kernel */
 #define XVEC_MAX_STACK 6           /* TDNN layers xvec_tdnn_stack can chain in one launch */
 #define XVEC_STACK_MAX_BANDS 512   /* scheduling bands of xvec_tdnn_stack (internal table size) */
@@ -104,7 +104,7 @@ XVEC_API int64_t xvec_splitk_workspace_bytes(int64_t rows, int cin, int taps, in
  * r and r*r into part_dev[slot][2][n] (float32).  BatchNorm of this layer is applied by xvec_pool_finalize.
  * replaces: TdnnLayer #5 (main.py:43) + the reads of torch.mean/torch.std in stat_pool (main.py:59-63).
  *   row_utt_dev        int32 (rows): utterance index of a row that takes part in pooling, -1 for don't-care rows
- *   blk_slot_base_dev  int32 (ceil(rows/256)*8): first partial slot of each 32-row block (slots of a block are
+ *   blk_slot_base_dev  int32 (ceil(rows/256)*2): first partial slot of each 128-row block (slots of a block are
  *                      consecutive, one per utterance with a pooled row in it, in row order)
  */
 XVEC_API int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin, int64_t x_ld,
@@ -113,7 +113,7 @@ XVEC_API int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows
                          float* part_dev, int64_t rows, void* stream);
 
 /* Expands per-utterance arrays (device, int32: first row, pooled-frame count, exclusive prefix sum of partial slots — see
- * xvec_tdnn_pool_fused) into row_utt_dev (rows) and blk_slot_base_dev (ceil(rows/256)*8) on the device, so a ragged batch
+ * xvec_tdnn_pool_fused) into row_utt_dev (rows) and blk_slot_base_dev (ceil(rows/256)*2) on the device, so a ragged batch
  * uploads 12 bytes per utterance instead of 4 bytes per frame.  The reference has no counterpart (fixed 3 s cuts, dataset.py:204). */
 XVEC_API int xvec_build_layout(const int32_t* starts_dev, const int32_t* n_pool_dev, const int32_t* slot_start_dev, int n_utts,
                       int64_t rows, int32_t* row_utt_dev, int32_t* blk_slot_base_dev, void* stream);

@@ -35,9 +35,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return r;
 }
 
-// Statistics-pooling epilogue of one accumulator tile for one epilogue warp (replaces the reads of torch.mean / torch.std
-// in stat_pool, main.py:59-63): 32 rows x 32 columns at a time, transposed through smem so that lane == column; column sums
-// of r = relu(acc + bias) and r^2 per utterance present in the 32-row block, packed f32x2 arithmetic, fixed order.
+// Statistics-pooling epilogue of one TRANSPOSED accumulator tile for one epilogue warp (replaces the reads of torch.mean /
+// torch.std in stat_pool, main.py:59-63).  The MMA warp swaps the operands of the pooled layer (weights = M operand, frames = N
+// operand; both are 128 rows x 128 bytes K-major, so it is only a swap of the two descriptors): TMEM lane = output channel,
+// column = frame.  A thread then owns ONE channel and reads 32 consecutive frames per tcgen05.ld, so the sums over time are
+// plain register adds — no shared-memory transpose, no shuffles.  The warp covers XVEC_POOL_BLOCK = 128 consecutive frames
+// (4 loads, load k+1 in flight while block k is reduced) and emits, per utterance with a pooled frame among them, the sum and
+// the sum of squares of r = relu(acc + bias) into part[slot][2][n]; slots of a 128-frame group are consecutive in row order
+// (blk_slot_base), the summation order is fixed (frame pairs in increasing order), nothing is atomic.
 struct PoolArgs {
   int rows, n;
   const float* bias;
@@ -45,77 +50,76 @@ struct PoolArgs {
   const int* blk_slot_base;
   float* part;
 };
-// tbase: TMEM address of this warp's lane quarter in the accumulator buffer; row0: first frame row of the warp's 32 rows;
-// [cbeg, cend): the warp's columns of the tile; tr: the warp's dense 32x32 fp32 transpose tile (XOR-swizzled by 4-row groups);
-// release(): called once, right after the warp's last tcgen05.ld of the tile has landed (it is NOT called when the warp
-// reads nothing — no pooled rows or no valid columns — the caller then releases the buffer itself).
+// tcol: TMEM address of (this warp's lane quarter, first of its 128 columns); ch: this thread's channel; f0: frame of column 0
+// (a multiple of 128); release(): called once, right after the warp's last tcgen05.ld of the tile has landed (NOT called when
+// none of the warp's channels exist — the caller then releases the buffer itself).
 template <class Release>
-__device__ __forceinline__ void pool_epilogue_tile(const PoolArgs& p, uint32_t tbase, int row0, int n0, int cbeg, int cend, float* tr,
-                                                   int lane, Release&& release) {
-  const int row = row0 + lane;
-  const int c_last = min(cend, p.n - n0) - 1;  // last valid column of this warp's range (may be < cbeg)
-  const int my_u = (row < p.rows) ? __ldg(p.row_utt + row) : -1;
-  const int slot0 = __ldg(p.blk_slot_base + (row0 >> 5));
-  const unsigned valid = __ballot_sync(0xffffffffu, my_u >= 0);
-  for (int c = cbeg; c < cend && n0 + c < p.n; c += 32) {
-    if (valid == 0u) break;  // block has no pooled rows (warp-uniform)
-    uint32_t v[32];
-    tmem_ld_32x32(tbase + c, v);
-    tmem_ld_wait();
-    if (c + 32 > c_last) release();
+__device__ __forceinline__ void pool_epilogue_tile_t(const PoolArgs& p, uint32_t tcol, int ch, int f0, int lane, Release&& release) {
+  if (ch - lane >= p.n) return;  // warp-uniform: none of the warp's 32 channels exist
+  const float bch = (ch < p.n && p.bias) ? __ldg(p.bias + ch) : 0.f;
+  const float2 b2 = make_float2(bch, bch);
+  int my_u[4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j)  // tr[column j][row lane], row group (lane/4) stored at slot (lane/4 ^ j%8)
-      tr[j * 32 + ((((lane >> 2) ^ (j & 7)) << 2) | (lane & 3))] = __uint_as_float(v[j]);
-    __syncwarp();
-    const int col = n0 + c + lane;  // this lane now owns one column
-    const float b = (col < p.n && p.bias) ? __ldg(p.bias + col) : 0.f;
-    float4 z[8];                    // the column's 32 rows
+  for (int k = 0; k < 4; ++k) {  // frame -> utterance of the four 32-frame blocks (lane = frame within the block)
+    const int f = f0 + 32 * k + lane;
+    my_u[k] = f < p.rows ? __ldg(p.row_utt + f) : -1;
+  }
+  int slot = __ldg(p.blk_slot_base + (f0 / XVEC_POOL_BLOCK));
+  float* const part_ch = p.part + ch;
+  const size_t slot_stride = 2 * static_cast<size_t>(p.n);
+  uint32_t va[32], vb[32];
+  tmem_ld_32x32(tcol, va);
+  tmem_ld_wait();
+  int cur_u = -1;  // utterance whose sums are being accumulated (frames of an utterance are consecutive rows)
+  float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) z[i] = *reinterpret_cast<const float4*>(tr + lane * 32 + ((i ^ (lane & 7)) << 2));
-    __syncwarp();
-    const float2 b2 = make_float2(b, b);
-    unsigned remaining = valid;
-    int seg = 0;
-    while (remaining) {  // one pass per utterance present in this 32-row block (warp-uniform)
+  for (int k = 0; k < 4; ++k) {
+    uint32_t(&v)[32] = (k & 1) ? vb : va;
+    if (k + 1 < 4) tmem_ld_32x32(tcol + 32 * (k + 1), (k & 1) ? va : vb);
+    unsigned remaining = __ballot_sync(0xffffffffu, my_u[k] >= 0);
+    while (remaining) {  // one pass per utterance present in this 32-frame block (warp-uniform)
       const int lo = __ffs(remaining) - 1;
-      const int u = __shfl_sync(0xffffffffu, my_u, lo);
-      const unsigned m = __ballot_sync(0xffffffffu, my_u == u);
-      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+      const int u = __shfl_sync(0xffffffffu, my_u[k], lo);
+      const unsigned m = __ballot_sync(0xffffffffu, my_u[k] == u);
+      if (u != cur_u) {
+        if (cur_u >= 0) {
+          if (ch < p.n) {
+            part_ch[slot * slot_stride] = s2.x + s2.y;
+            part_ch[slot * slot_stride + p.n] = q2.x + q2.y;
+          }
+          ++slot;
+        }
+        cur_u = u;
+        s2 = make_float2(0.f, 0.f);
+        q2 = make_float2(0.f, 0.f);
+      }
       if (m == 0xffffffffu) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float2 a = __fadd2_rn(make_float2(z[i].x, z[i].y), b2);
-          float2 d = __fadd2_rn(make_float2(z[i].z, z[i].w), b2);
-          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f);
-          d.x = fmaxf(d.x, 0.f); d.y = fmaxf(d.y, 0.f);
+        for (int j = 0; j < 32; j += 2) {
+          float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), b2);
+          a.x = fmaxf(a.x, 0.f);
+          a.y = fmaxf(a.y, 0.f);
           s2 = __fadd2_rn(s2, a);
           q2 = __ffma2_rn(a, a, q2);
-          s2 = __fadd2_rn(s2, d);
-          q2 = __ffma2_rn(d, d, q2);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float2 a = __fadd2_rn(make_float2(z[i].x, z[i].y), b2);
-          float2 d = __fadd2_rn(make_float2(z[i].z, z[i].w), b2);
-          a.x = ((m >> (4 * i + 0)) & 1u) ? fmaxf(a.x, 0.f) : 0.f;
-          a.y = ((m >> (4 * i + 1)) & 1u) ? fmaxf(a.y, 0.f) : 0.f;
-          d.x = ((m >> (4 * i + 2)) & 1u) ? fmaxf(d.x, 0.f) : 0.f;
-          d.y = ((m >> (4 * i + 3)) & 1u) ? fmaxf(d.y, 0.f) : 0.f;
+        for (int j = 0; j < 32; j += 2) {
+          float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), b2);
+          a.x = ((m >> j) & 1u) ? fmaxf(a.x, 0.f) : 0.f;
+          a.y = ((m >> (j + 1)) & 1u) ? fmaxf(a.y, 0.f) : 0.f;
           s2 = __fadd2_rn(s2, a);
           q2 = __ffma2_rn(a, a, q2);
-          s2 = __fadd2_rn(s2, d);
-          q2 = __ffma2_rn(d, d, q2);
         }
       }
-      if (col < p.n) {
-        float* dst = p.part + static_cast<size_t>(slot0 + seg) * 2 * p.n + col;
-        dst[0] = s2.x + s2.y;
-        dst[p.n] = q2.x + q2.y;
-      }
       remaining &= ~m;
-      ++seg;
     }
+    if (k + 1 < 4) tmem_ld_wait();
+    if (k == 2) release();  // the last tcgen05.ld of the tile has landed
+  }
+  if (cur_u >= 0 && ch < p.n) {
+    part_ch[slot * slot_stride] = s2.x + s2.y;
+    part_ch[slot * slot_stride + p.n] = q2.x + q2.y;
   }
 }
 

@@ -79,34 +79,46 @@ pool_finalize_kernel(const float* __restrict__ part, const int* __restrict__ slo
                      void* __restrict__ out_lp, int lp_dtype, long long lp_ld) {
   const int u = blockIdx.x;
   const int col = blockIdx.y * 128 + threadIdx.x;
+  __shared__ double inv_n[2];
+  if (threadIdx.x == 0) {
+    const int n0 = n_rows[u];
+    inv_n[0] = n0 > 0 ? 1.0 / n0 : 0.0;
+    inv_n[1] = n0 > 1 ? 1.0 / (n0 - 1) : 0.0;
+  }
+  __syncthreads();
   if (col >= p) return;
   const int sl0 = slot_start[u], sl1 = slot_start[u + 1];
   double S = 0.0, Q = 0.0;
   int sl = sl0;
-  for (; sl < sl1; sl += 12) {  // up to 24 independent loads in flight (a 3 s utterance has ~10 slots), summed in slot order
-    float a[12], b[12];
+  for (; sl + 4 <= sl1; sl += 4) {  // 8 independent loads in flight, summed in slot order
+    float a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const bool ok = sl + i < sl1;
-      const float* src = part + static_cast<size_t>(ok ? sl + i : sl) * 2 * p + col;
-      a[i] = ok ? src[0] : 0.f;
-      b[i] = ok ? src[p] : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const float* src = part + static_cast<size_t>(sl + i) * 2 * p + col;
+      a[i] = src[0];
+      b[i] = src[p];
     }
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < 4; ++i) {
       S += static_cast<double>(a[i]);
       Q += static_cast<double>(b[i]);
     }
   }
+  for (; sl < sl1; ++sl) {  // a 3 s utterance has 3-4 slots of 128 frames
+    const float* src = part + static_cast<size_t>(sl) * 2 * p + col;
+    S += static_cast<double>(src[0]);
+    Q += static_cast<double>(src[p]);
+  }
+  // 1/n and 1/(n-1) once per block (float64 division is a long software sequence; per thread it dominated this kernel)
   const int n = n_rows[u];
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  double mean = n > 0 ? S / n : nan;
-  double var = n > 1 ? (Q - S * S / n) / (n - 1) : nan;  // torch.std: unbiased; a single frame gives NaN
+  const double mean = n > 0 ? S * inv_n[0] : nan;
+  double var = n > 1 ? (Q - S * S * inv_n[0]) * inv_n[1] : nan;  // torch.std: unbiased; a single frame gives NaN
   if (var < 0.0) var = 0.0;
   const float sc = scale ? scale[col] : 1.f;
   const float sh = shift ? shift[col] : 0.f;
   const float m = static_cast<float>(mean * sc + sh);
-  const float sd = static_cast<float>(fabs(static_cast<double>(sc)) * sqrt(var));
+  const float sd = fabsf(sc) * sqrtf(static_cast<float>(var));  // the cancellation is resolved in float64, the root in float32
   out[static_cast<size_t>(u) * 2 * p + col] = m;
   out[static_cast<size_t>(u) * 2 * p + p + col] = sd;
   if (out_lp) {
@@ -123,10 +135,10 @@ pool_finalize_kernel(const float* __restrict__ part, const int* __restrict__ slo
 }
 
 // ------------------------------------------------------------------------------------------------ layout expansion
-// Expands per-utterance arrays into the per-row / per-32-row-block bookkeeping of the fused pooling epilogue, on the device
+// Expands per-utterance arrays into the per-row / per-128-row-block bookkeeping of the fused pooling epilogue, on the device
 // (a ragged batch then only uploads 3 small per-utterance arrays instead of 4 bytes per frame).
 //   row_utt[r]        = u if row r is one of the first n_pool[u] rows of utterance u, else -1
-//   blk_slot_base[b]  = partial slot of the first utterance with a pooled row in 32-row block b
+//   blk_slot_base[b]  = partial slot of the first utterance with a pooled row in 128-row block b
 __global__ void __launch_bounds__(256)
 build_layout_kernel(const int* __restrict__ starts, const int* __restrict__ n_pool, const int* __restrict__ slot_start, int n_utts,
                     int rows, int n_blocks, int* __restrict__ row_utt, int* __restrict__ blk_slot_base) {
@@ -243,7 +255,7 @@ int xvec_build_layout(const int32_t* starts_dev, const int32_t* n_pool_dev, cons
   if (rc) return rc;
   if (!starts_dev || !n_pool_dev || !slot_start_dev || !row_utt_dev || !blk_slot_base_dev) return set_error(XVEC_E_ARG, "null pointer argument");
   if (n_utts <= 0 || rows <= 0 || rows > 0x7fffff00LL) return set_error(XVEC_E_ARG, "bad n_utts / rows");
-  const int n_blocks = static_cast<int>((rows + 255) / 256) * 8;
+  const int n_blocks = static_cast<int>((rows + 255) / 256) * (256 / XVEC_POOL_BLOCK);
   const long long n = rows > n_blocks ? rows : n_blocks;
   build_layout_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       starts_dev, n_pool_dev, slot_start_dev, n_utts, static_cast<int>(rows), n_blocks, row_utt_dev, blk_slot_base_dev);

@@ -72,7 +72,7 @@ constexpr int num_stages() {
 }
 template <int kEpi>
 constexpr int epi_smem_bytes() {
-  return kEpi == EPI_POOL ? EPI_WARPS * 32 * 32 * 4 : EPI_WARPS * OUT_BUFS * OUT_BUF_BYTES;  // pool: dense 32x32 fp32 transpose tiles
+  return kEpi == EPI_POOL ? 0 : EPI_WARPS * OUT_BUFS * OUT_BUF_BYTES;  // the pooling epilogue works in registers
 }
 template <int kEpi>
 constexpr int gemm_smem_bytes() {
@@ -192,8 +192,9 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           if (kb == kb0 && lane == 0) trace(p, it, 3);
           const uint32_t a_addr = smem_u32(base + stage * STAGE_BYTES);
-          const uint64_t da = umma_desc_sw128(a_addr);
-          const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
+          // EPI_POOL computes the tile transposed (weights = M operand): see pool_epilogue_tile_t
+          const uint64_t da = umma_desc_sw128(kEpi == EPI_POOL ? a_addr + A_BYTES : a_addr);
+          const uint64_t db = umma_desc_sw128(kEpi == EPI_POOL ? a_addr : a_addr + A_BYTES);
           int stage_n = stage + 1;
           uint32_t phase_n = phase;
           if (stage_n == STAGES) { stage_n = 0; phase_n ^= 1u; }
@@ -247,9 +248,9 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int c_last = min(cend, p.n - n0) - 1;  // last valid column of this warp's range (may be < cbeg)
 
       if constexpr (kEpi == EPI_POOL) {
-        float* tr = reinterpret_cast<float*>(epi_smem) + (warp - 2) * (32 * 32);
         const PoolArgs pa{p.rows, p.n, p.bias, p.row_utt, p.blk_slot_base, p.part};
-        pool_epilogue_tile(pa, tbase, row0, n0, cbeg, cend, tr, lane, release_tmem);
+        pool_epilogue_tile_t(pa, tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + cbeg,
+                             n0 + static_cast<int>(rank) * BN_CTA + q * 32 + lane, (tt / p.n_tiles) * BM + cbeg, lane, release_tmem);
       } else {
         uint8_t* out_stage = epi_smem + (warp - 2) * (OUT_BUFS * OUT_BUF_BYTES);  // 32-row x 128-byte staging boxes
         constexpr int OUT_ES = kEpi == EPI_STORE_BF16 ? 2 : 4;

@@ -423,70 +423,11 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       };
 
       if (layer == p.n_layers - 1) {
-        // Last layer: statistics-pooling partials (replaces the reads of torch.mean / torch.std in stat_pool, main.py:59-63);
-        // nothing is stored and nobody waits for this tile.  The accumulator is TRANSPOSED (the MMA warp swapped the operands):
-        // TMEM lane = output channel, column = frame, so a thread holds 32 consecutive frames of ONE channel and the sums over
-        // time are plain register adds — no shared-memory transpose, no shuffles.  Per 32-frame block and utterance present in
-        // it: sum and sum of squares of r = relu(acc + bias) in the same pairwise order as pool_epilogue_tile (bit-identical).
-        const int ch = n0 + static_cast<int>(rank) * BN_CTA + q * 32 + lane;  // this thread's channel
-        const int ch_warp = ch - lane;
-        if (ch_warp < L.n) {  // warp-uniform: some of the warp's channels exist
-          const float bch = ch < L.n ? __ldg(L.bias + ch) : 0.f;
-          const float2 b2 = make_float2(bch, bch);
-          const int f0 = mt * BM + cbeg;  // first frame of this warp's 128 columns
-          int my_u[4], slot0[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // frame -> utterance of the four 32-frame blocks (lane = frame within the block)
-            const int f = f0 + 32 * k + lane;
-            my_u[k] = f < p.rows ? __ldg(p.row_utt + f) : -1;
-            slot0[k] = __ldg(p.blk_slot_base + ((f0 + 32 * k) >> 5));
-          }
-          const uint32_t tcol = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + cbeg;
-          uint32_t va[32], vb[32];
-          tmem_ld_32x32(tcol, va);
-          tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint32_t(&v)[32] = (k & 1) ? vb : va;
-            if (k + 1 < 4) tmem_ld_32x32(tcol + 32 * (k + 1), (k & 1) ? va : vb);  // in flight while block k is reduced
-            unsigned remaining = __ballot_sync(0xffffffffu, my_u[k] >= 0);
-            int seg = 0;
-            while (remaining) {  // one pass per utterance present in this 32-frame block (warp-uniform)
-              const int lo = __ffs(remaining) - 1;
-              const int u = __shfl_sync(0xffffffffu, my_u[k], lo);
-              const unsigned m = __ballot_sync(0xffffffffu, my_u[k] == u);
-              float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-              if (m == 0xffffffffu) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                  float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), b2);
-                  a.x = fmaxf(a.x, 0.f);
-                  a.y = fmaxf(a.y, 0.f);
-                  s2 = __fadd2_rn(s2, a);
-                  q2 = __ffma2_rn(a, a, q2);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                  float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), b2);
-                  a.x = ((m >> j) & 1u) ? fmaxf(a.x, 0.f) : 0.f;
-                  a.y = ((m >> (j + 1)) & 1u) ? fmaxf(a.y, 0.f) : 0.f;
-                  s2 = __fadd2_rn(s2, a);
-                  q2 = __ffma2_rn(a, a, q2);
-                }
-              }
-              if (ch < L.n) {
-                float* dst = p.part + static_cast<size_t>(slot0[k] + seg) * 2 * L.n + ch;
-                dst[0] = s2.x + s2.y;
-                dst[L.n] = q2.x + q2.y;
-              }
-              remaining &= ~m;
-              ++seg;
-            }
-            if (k + 1 < 4) tmem_ld_wait();
-            if (k == 2) release_tmem();  // the last tcgen05.ld of the tile has landed
-          }
-        }
+        // Last layer: statistics-pooling partials; nothing is stored and nobody waits for this tile.  The accumulator is
+        // TRANSPOSED (the MMA warp swapped the operands): TMEM lane = output channel, column = frame (gemm_tile.cuh).
+        const PoolArgs pa{p.rows, L.n, L.bias, p.row_utt, p.blk_slot_base, p.part};
+        pool_epilogue_tile_t(pa, tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + cbeg,
+                             n0 + static_cast<int>(rank) * BN_CTA + q * 32 + lane, mt * BM + cbeg, lane, release_tmem);
         if (!released) release_tmem();
         if (pend) flush();  // its stores were issued a whole tile ago
       } else {

@@ -24,7 +24,7 @@ class FrameLayout:
     n_pool: np.ndarray           # int32 (U) pooled frames per utterance
     rows: int                    # total rows
     row_utt: np.ndarray          # int32 (rows) utterance of a pooled row, -1 for don't-care rows
-    blk_slot_base: np.ndarray    # int32 (ceil(rows/256)*8) first partial slot of each 32-row block
+    blk_slot_base: np.ndarray    # int32 (ceil(rows/256)*2) first partial slot of each 128-row block
     utt_slot_start: np.ndarray   # int32 (U+1) partial slots of utterance u are [utt_slot_start[u], utt_slot_start[u+1])
     n_slots: int
 
@@ -56,7 +56,7 @@ def build_layout(lengths, lost_frames: int = TOTAL_CONTEXT) -> FrameLayout:
     # block index of every slot, in slot order (non-decreasing)
     slot_utt = np.repeat(np.arange(lengths.size, dtype=np.int64), cnt)
     slot_block = b0[slot_utt] + (np.arange(n_slots, dtype=np.int64) - utt_slot_start[slot_utt])
-    n_blocks = ((rows + 255) // 256) * 8  # the GEMM tiles 256 rows per CTA pair
+    n_blocks = ((rows + 255) // 256) * (256 // blk)  # the GEMM tiles 256 rows per CTA pair
     blk_slot_base = np.searchsorted(slot_block, np.arange(n_blocks, dtype=np.int64), side="left").astype(np.int32)
     return FrameLayout(lengths, starts, n_pool.astype(np.int32), rows, row_utt, blk_slot_base, utt_slot_start.astype(np.int32), n_slots)
 

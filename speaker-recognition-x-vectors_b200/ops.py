@@ -98,7 +98,7 @@ def tdnn_pool_fused(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
     rows = x.shape[0]
     if row_utt.dtype != torch.int32 or blk_slot_base.dtype != torch.int32 or part.dtype != torch.float32:
         raise ValueError("row_utt / blk_slot_base must be int32, part float32")
-    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * 8 or not part.is_contiguous():
+    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * (256 // _lib.POOL_BLOCK) or not part.is_contiguous():
         raise ValueError("pooling bookkeeping arrays are too small for this frame matrix")
     offs = taps_array(offsets)
     with torch.cuda.device(x.device):
@@ -120,7 +120,7 @@ def tdnn_stack(layer_descs, n_layers: int, x: torch.Tensor, act0: torch.Tensor, 
         raise ValueError("x must be float32; act0 / act1 must share dtype and row stride")
     if act0.shape[0] < rows or act1.shape[0] < rows:
         raise ValueError("activation buffers are too small for this frame matrix")
-    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * 8 or not part.is_contiguous():
+    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * (256 // _lib.POOL_BLOCK) or not part.is_contiguous():
         raise ValueError("pooling bookkeeping arrays are too small for this frame matrix")
     with torch.cuda.device(x.device):
         check(lib.xvec_tdnn_stack(layer_descs, n_layers, ptr(x), rows, x_ld, ptr(act0), ptr(act1), act_ld, ptr(row_utt), ptr(blk_slot_base),
@@ -155,7 +155,7 @@ def build_layout_device(starts: torch.Tensor, n_pool: torch.Tensor, slot_start: 
     lib = _lib.load()
     if any(t.dtype != torch.int32 or not t.is_contiguous() for t in (starts, n_pool, slot_start, row_utt, blk_slot_base)):
         raise ValueError("layout arrays must be contiguous int32")
-    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * 8 or slot_start.numel() < starts.numel() + 1:
+    if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * (256 // _lib.POOL_BLOCK) or slot_start.numel() < starts.numel() + 1:
         raise ValueError("layout output arrays are too small")
     with torch.cuda.device(starts.device):
         check(lib.xvec_build_layout(ptr(starts), ptr(n_pool), ptr(slot_start), starts.numel(), rows, ptr(row_utt), ptr(blk_slot_base),

@@ -42,7 +42,7 @@ class _Layout:
         staging.mark()
         self.starts, self.n_pool, self.utt_slot_start = dev[:u], dev[u:2 * u], dev[2 * u:]
         self.row_utt = torch.empty(rows, dtype=torch.int32, device=device)
-        self.blk_slot_base = torch.empty(((rows + 255) // 256) * 8, dtype=torch.int32, device=device)
+        self.blk_slot_base = torch.empty(((rows + 255) // 256) * (256 // _lib.POOL_BLOCK), dtype=torch.int32, device=device)
         ops.build_layout_device(self.starts, self.n_pool, self.utt_slot_start, rows, self.row_utt, self.blk_slot_base)
 
 

@@ -42,12 +42,13 @@ def test_fails_loudly_without_gpu():
 
 
 def _emulate_fused_pool(lay, r):
-    """numpy model of the EPI_POOL epilogue + finalize: per 32-row block, per utterance present -> one slot."""
+    """numpy model of the EPI_POOL epilogue + finalize: per 128-row block, per utterance present -> one slot."""
     P = r.shape[1]
     part = np.full((lay.n_slots, 2, P), np.nan)
-    n_blocks = (lay.rows + 31) // 32
+    B = xvec_b200._lib.POOL_BLOCK
+    n_blocks = (lay.rows + B - 1) // B
     for b in range(n_blocks):
-        rows = np.arange(b * 32, min(lay.rows, b * 32 + 32))
+        rows = np.arange(b * B, min(lay.rows, b * B + B))
         us = lay.row_utt[rows]
         seg = 0
         for u in sorted(set(us[us >= 0].tolist())):
@@ -78,7 +79,7 @@ def test_layout_bookkeeping_is_exact(lens):
     assert (lay.n_pool == np.asarray(lens) - 14).all()
     for u, (s, l) in enumerate(zip(lay.starts, lens)):
         assert (lay.row_utt[s:s + l - 14] == u).all() and (lay.row_utt[s + l - 14:s + l] == -1).all()
-    assert lay.blk_slot_base.shape[0] == -(-lay.rows // 256) * 8
+    assert lay.blk_slot_base.shape[0] == -(-lay.rows // 256) * (256 // xvec_b200._lib.POOL_BLOCK)
     rng = np.random.default_rng(0)
     r = np.abs(rng.standard_normal((lay.rows, 8)))
     got = _emulate_fused_pool(lay, r)
