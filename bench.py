@@ -277,8 +277,9 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE tdnn_stack_kernel launch on this workload (ncu --set full, profiles/)
-STACK_DRAM_BYTES = {}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE tdnn_stack_kernel launch on this workload
+# (ncu --set full, profiles/r01_v10_ncu_full_summary.txt: 83.7 MB read + 272.3 MB written; the four 78.6 MB activations are written once)
+STACK_DRAM_BYTES = {"bf16": 355921408}
 
 
 def instrumented_stack_time(model, x_dev, lengths, n_batches, iters):
