@@ -39,6 +39,19 @@ class HostExtractor:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    def reserve(self, max_rows: int, max_utts: int, channels: int) -> None:
+        """Size the staging buffer, the pinned result buffer and the model scratch of every slot for batches of up to
+        max_rows frames / max_utts utterances (allocation synchronises the device; do it before the pipeline runs)."""
+        dim = (self.model.segment_layer7 if self.model.x_vec_extract_layer == 7 else self.model.segment_layer6).out_features
+        pooled_slots = max_rows // 128 + max_utts + 2  # partial slots: one per 128-frame group + one per utterance boundary
+        with torch.cuda.device(self.device):
+            for i, sl in enumerate(self.slots):
+                if sl.x_dev is None or sl.x_dev.shape[0] < max_rows or sl.x_dev.shape[1] != channels:
+                    sl.x_dev = torch.empty((max_rows, channels), dtype=torch.float32, device=self.device)
+                if sl.out_host is None or sl.out_host.shape[0] < max_utts or sl.out_host.shape[1] != dim:
+                    sl.out_host = torch.empty((max_utts, dim), dtype=torch.float32, pin_memory=True)
+                self.model._scratch_for(i).ensure(max_rows, pooled_slots, max_utts)
+
     def submit(self, x_host: torch.Tensor, lengths) -> int:
         """Enqueue one batch: x_host is a float32 host tensor (rows, C) or (B, T, C), ideally pinned.  Returns a ticket."""
         if x_host.is_cuda:
@@ -99,15 +112,21 @@ class HostExtractor:
                     out = np.empty((len(lengths), r.shape[1]), dtype=np.float64)
                 out[lo:hi] = r
 
+        # plan the batches first, so that every slot's buffers can be sized once for the largest batch: growing a slot's
+        # scratch in the middle of the run costs a cudaFree + cudaMalloc (device-wide synchronisation) per growth
+        plan = []
         lo = 0
         n = len(lengths)
         while lo < n:
             row0 = int(ends[lo - 1]) if lo else 0
             hi = int(np.searchsorted(ends, row0 + max_frames, side="right"))
             hi = max(lo + 1, min(hi, lo + max_utts, n))
-            drain(len(self.slots) - 1)
-            pending.append((self.submit(flat_host[row0:int(ends[hi - 1])], lengths[lo:hi]), lo, hi))
+            plan.append((lo, hi, row0, int(ends[hi - 1])))
             lo = hi
+        self.reserve(max(r1 - r0 for _, _, r0, r1 in plan), max(hi - lo for lo, hi, _, _ in plan), flat_host.shape[1])
+        for lo, hi, row0, row1 in plan:
+            drain(len(self.slots) - 1)
+            pending.append((self.submit(flat_host[row0:row1], lengths[lo:hi]), lo, hi))
         drain(0)
         return out
 

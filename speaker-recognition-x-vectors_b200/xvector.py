@@ -164,7 +164,7 @@ class XVectorModel(nn.Module):
         key = (lengths.tobytes(), str(dev), torch.cuda.current_stream().cuda_stream)
         lay = self._layouts.get(key)
         if lay is None:
-            st = self._scratch.setdefault(("pin", key[2]), _PinnedStaging())
+            st = self._scratch.setdefault(("pin", key[1]), _PinnedStaging())  # one ring per device: its buffers are event-guarded
             lay = _Layout(lengths, self.lost_frames, dev, st)
             self._layouts[key] = lay
             while len(self._layouts) > 128:
