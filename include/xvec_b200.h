@@ -220,6 +220,23 @@ XVEC_API int xvec_cast(const float* src_dev, int64_t src_ld, void* dst_dev, int 
 XVEC_API int xvec_cosine_trials(const float* xvec_dev, int64_t ld, int dim, const float* mean_dev, const int32_t* enrol_dev,
                        const int32_t* test_dev, int64_t n_trials, float* out_dev, void* stream);
 
+/* PLDA log-likelihood-ratio scoring of trials (two-covariance model mean / F / Sigma), without the N x N score matrix:
+ *   score[t] = scale * ( q[e] + q[s] + <p_e, x_s - mean> + cst ),   q_i = 1/2 <x_i - mean, (x_i - mean) Phi>,   p = (x - mean) Psi
+ * replaces: plda_classifier.plda_scores (plda_classifier.py:81-87, speechbrain.processing.PLDA_LDA.fast_PLDA_scoring) + the
+ * per-trial lookup loop plda_score_stat.py:59-87.  Phi, Psi, cst come from the model on the host (float64, once per model);
+ * y = (x - mean) Phi and p = (x - mean) Psi are two xvec_tdnn_layer GEMMs (taps = 1, bias = -mean Phi / -mean Psi) run as
+ * split-TF32: xvec_split_tf32 writes [hi(x) | x - hi(x) | hi(x)] (hi = TF32-exact part) and the weights are packed as
+ * [W_hi | W_hi | W_lo], so one TF32 GEMM over K = 3 dim gives x W to ~2^-21 relative (plain TF32 would move scores by 1e-3 of
+ * their magnitude — more than the gap between neighbouring trial scores at the decision threshold).
+ * SpeechBrain is not vendored with the reference: parity for these two entry points is UNPINNED (checked against
+ * oracle/plda_oracle.py, which is itself checked against the model's Gaussian definition). */
+XVEC_API int xvec_split_tf32(const float* x_dev, int64_t ld, int64_t rows, int cols, float* out_dev, int64_t out_ld, void* stream);
+XVEC_API int xvec_plda_rowterm(const float* x_dev, int64_t ld, int dim, const float* mean_dev, const float* y_dev, int64_t y_ld,
+                      int64_t n, float* q_dev, void* stream);
+XVEC_API int xvec_plda_trials(const float* x_dev, int64_t ld, int dim, const float* mean_dev, const float* p_dev, int64_t p_ld,
+                     const float* q_dev, const int32_t* enrol_dev, const int32_t* test_dev, int64_t n_trials, float cst, float scale,
+                     float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,10 @@ _SIGNATURES = {
     "xvec_wav_minmax": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "xvec_cast": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p]),
     "xvec_cosine_trials": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "xvec_split_tf32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "xvec_plda_rowterm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "xvec_plda_trials": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                                 c_void_p, c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -231,6 +231,54 @@ cosine_trials_kernel(const float* __restrict__ xv, long long ld, int dim, const 
   if (lane == 0) out[t] = ab * rsqrtf(aa) * rsqrtf(bb);
 }
 
+// ------------------------------------------------------------------------------------------------ PLDA trials
+// out[r] = [hi(x_r) | x_r - hi(x_r) | hi(x_r)], hi = x with the 13 low mantissa bits cleared (exactly representable in TF32).
+// With weights [W_hi ; W_hi ; W_lo] one TF32 GEMM over K = 3*cols computes x_hi W_hi + x_lo W_hi + x_hi W_lo, i.e. x W to ~2^-21.
+__global__ void split_tf32_kernel(const float* __restrict__ x, long long ld, long long rows, int cols, float* __restrict__ out, long long out_ld) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const float v = x[r * ld + c];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    float* o = out + r * out_ld + c;
+    o[0] = hi;
+    o[cols] = v - hi;
+    o[2 * cols] = hi;
+  }
+}
+// q[i] = 1/2 <x_i - mean, y_i>   (y = (x - mean) Phi from the GEMM kernel): one warp per row
+__global__ void __launch_bounds__(256)
+plda_rowterm_kernel(const float* __restrict__ x, long long ld, int dim, const float* __restrict__ mean, const float* __restrict__ y,
+                    long long y_ld, long long n, float* __restrict__ q) {
+  const long long r = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float acc = 0.f;
+  for (int i = lane; i < dim; i += 32) acc = fmaf(x[r * ld + i] - mean[i], y[r * y_ld + i], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) q[r] = 0.5f * acc;
+}
+// score[t] = scale * (q[e] + q[s] + <p_e, x_s - mean> + cst)   (p = (x - mean) Psi): one warp per trial
+__global__ void __launch_bounds__(256)
+plda_trials_kernel(const float* __restrict__ x, long long ld, int dim, const float* __restrict__ mean, const float* __restrict__ p,
+                   long long p_ld, const float* __restrict__ q, const int* __restrict__ enrol, const int* __restrict__ test,
+                   long long n_trials, float cst, float scale, float* __restrict__ out) {
+  const long long t = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= n_trials) return;
+  const int e = enrol[t], s = test[t];
+  const float* pe = p + static_cast<long long>(e) * p_ld;
+  const float* xs = x + static_cast<long long>(s) * ld;
+  float acc = 0.f;
+  for (int i = lane; i < dim; i += 32) acc = fmaf(pe[i], xs[i] - mean[i], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[t] = scale * (q[e] + q[s] + acc + cst);
+}
+
 static int grid_for(long long total) {
   const long long want = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -338,6 +386,39 @@ int xvec_cosine_trials(const float* xvec_dev, int64_t ld, int dim, const float* 
   cosine_trials_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(xvec_dev, ld, dim, mean_dev, enrol_dev,
                                                                                                    test_dev, n_trials, out_dev);
   return check_launch("cosine_trials_kernel");
+}
+
+int xvec_split_tf32(const float* x_dev, int64_t ld, int64_t rows, int cols, float* out_dev, int64_t out_ld, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!x_dev || !out_dev) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (rows <= 0 || cols <= 0 || ld < cols || out_ld < 3 * static_cast<int64_t>(cols)) return set_error(XVEC_E_ARG, "bad shape");
+  split_tf32_kernel<<<grid_for(rows * cols), 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, ld, rows, cols, out_dev, out_ld);
+  return check_launch("split_tf32_kernel");
+}
+
+int xvec_plda_rowterm(const float* x_dev, int64_t ld, int dim, const float* mean_dev, const float* y_dev, int64_t y_ld, int64_t n,
+                      float* q_dev, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!x_dev || !mean_dev || !y_dev || !q_dev) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (dim <= 0 || ld < dim || y_ld < dim || n <= 0) return set_error(XVEC_E_ARG, "bad shape");
+  const long long blocks = (n * 32 + 255) / 256;
+  plda_rowterm_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, ld, dim, mean_dev, y_dev, y_ld, n, q_dev);
+  return check_launch("plda_rowterm_kernel");
+}
+
+int xvec_plda_trials(const float* x_dev, int64_t ld, int dim, const float* mean_dev, const float* p_dev, int64_t p_ld, const float* q_dev,
+                     const int32_t* enrol_dev, const int32_t* test_dev, int64_t n_trials, float cst, float scale, float* out_dev,
+                     void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!x_dev || !mean_dev || !p_dev || !q_dev || !enrol_dev || !test_dev || !out_dev) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (dim <= 0 || ld < dim || p_ld < dim || n_trials <= 0) return set_error(XVEC_E_ARG, "bad shape");
+  const long long blocks = (n_trials * 32 + 255) / 256;
+  plda_trials_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, ld, dim, mean_dev, p_dev, p_ld, q_dev,
+                                                                                                 enrol_dev, test_dev, n_trials, cst, scale, out_dev);
+  return check_launch("plda_trials_kernel");
 }
 
 }  // extern "C"

@@ -263,3 +263,31 @@ def cosine_trials(xvecs: torch.Tensor, enrol: torch.Tensor, test: torch.Tensor, 
         check(lib.xvec_cosine_trials(ptr(xvecs), ld, xvecs.shape[1], ptr(mean), ptr(enrol.contiguous()), ptr(test.contiguous()), n,
                                      ptr(out), stream_ptr()))
     return out
+
+
+def plda_trials(xvecs: torch.Tensor, mean: torch.Tensor, w_phi: torch.Tensor, b_phi: torch.Tensor, w_psi: torch.Tensor, b_psi: torch.Tensor,
+                cst: float, scale: float, enrol: torch.Tensor, test: torch.Tensor) -> torch.Tensor:
+    """PLDA log-likelihood-ratio of every (enrol, test) index pair into xvecs (N, D) float32; float32 (n_trials).
+    w_phi / w_psi: [W_hi | W_hi | W_lo] of W = Phi' / Psi' packed with pack_weight(…, 1, 3 D, float32) for the split-TF32
+    GEMMs (include/xvec_b200.h); b_phi / b_psi: -mean Phi / -mean Psi (pad32)."""
+    _require_cuda(xvecs, mean, w_phi, b_phi, w_psi, b_psi, enrol, test)
+    lib = _lib.load()
+    if xvecs.dtype != torch.float32 or enrol.dtype != torch.int32 or test.dtype != torch.int32:
+        raise ValueError("xvecs must be float32, trial indices int32")
+    ld = _rowmajor_2d(xvecs, "xvecs")
+    n, d = xvecs.shape
+    if test.numel() != enrol.numel():
+        raise ValueError("enrol and test must have the same length")
+    x = xvecs
+    x3 = torch.empty((n, 3 * d), dtype=torch.float32, device=x.device)  # [hi | lo | hi]: split-TF32 operand of both GEMMs
+    with torch.cuda.device(x.device):
+        check(lib.xvec_split_tf32(ptr(x), ld, n, d, ptr(x3), x3.stride(0), stream_ptr()))
+    y = tdnn_layer_flat(x3, w_phi, d, [0], b_phi, None, None, relu=False, out_dtype=torch.float32, cin=3 * d)  # (x - mean) Phi
+    p = tdnn_layer_flat(x3, w_psi, d, [0], b_psi, None, None, relu=False, out_dtype=torch.float32, cin=3 * d)  # (x - mean) Psi
+    q = torch.empty(n, dtype=torch.float32, device=x.device)
+    out = torch.empty(enrol.numel(), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.xvec_plda_rowterm(ptr(x), x.stride(0), d, ptr(mean), ptr(y), y.stride(0), n, ptr(q), stream_ptr()))
+        check(lib.xvec_plda_trials(ptr(x), x.stride(0), d, ptr(mean), ptr(p), p.stride(0), ptr(q), ptr(enrol.contiguous()),
+                                   ptr(test.contiguous()), enrol.numel(), float(cst), float(scale), ptr(out), stream_ptr()))
+    return out

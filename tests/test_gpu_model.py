@@ -163,3 +163,31 @@ def test_scoring_module_trial_file(xb, state_dict):
     assert 0.0 <= d <= e + 1e-9 <= 0.5
     with pytest.raises(ValueError):
         scoring.score_trial_file(xv, ids, ["1 nope/a/b.wav " + ids[0] + "\n"])
+
+
+def test_plda_trial_scores_and_decisions(xb):
+    """PldaScorer (two split-TF32 GEMMs + xvec_plda_rowterm / xvec_plda_trials) against the float64 oracle on a synthetic model of
+    the reference's size (x-vector dim 512, rank_f 150, plda_classifier.py:40): score error far inside the decision margin of
+    the float64 scores at their EER threshold, identical decisions.  (Parity with SpeechBrain itself is unpinned.)"""
+    from oracle import plda_oracle as po
+    from xvec_b200 import scoring
+    d, rank, nspk, per = 512, 150, 40, 12
+    mean, F, S = po.synth_plda(d, rank, seed=5)
+    F = 0.3 * F  # speaker variability small enough for a non-trivial EER (~3 %) and a narrow decision margin (~7e-3 of scores up to 48)
+    rng = np.random.default_rng(6)
+    spk = np.arange(nspk * per) % nspk  # the round-robin speaker assignment synth_trials assumes
+    y = rng.standard_normal((nspk, rank))[spk]
+    xs = (mean + y @ F.T + rng.standard_normal((nspk * per, d)) @ np.linalg.cholesky(S).T).astype(np.float32)
+    enrol, test, target = ox.synth_trials(nspk * per, 8000, n_speakers=nspk, seed=4)
+    ref = po.trial_scores(xs.astype(np.float64), enrol, test, mean, F, S, scaling_factor=1.0)
+    eer, thr, margin = ox.eer_threshold_np(ref, target)
+    assert 0.01 < eer < 0.06
+    sc = scoring.PldaScorer(mean, F, S, scaling_factor=1.0)
+    got = sc.score_trials(torch.from_numpy(xs).cuda(), enrol, test)
+    err = np.abs(got - ref).max()
+    assert err < 2e-5 * np.abs(ref).max(), (err, np.abs(ref).max())  # split-TF32 GEMMs + float32 dots
+    assert err < margin, (err, margin)
+    assert np.array_equal(got >= thr, ref >= thr)
+    assert abs(scoring.eer(got, target)[0] - scoring.eer(ref, target)[0]) < 1e-9
+    with pytest.raises(ValueError):
+        sc.score_trials(torch.zeros(4, 100).cuda(), [0], [1])

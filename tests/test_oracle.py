@@ -134,3 +134,26 @@ def test_trials_and_eer_threshold():
 
 def test_flops_formula():
     assert abs(ox.flops_per_utt(300) / 1.5378e9 - 1) < 1e-3
+
+
+def test_plda_fast_scoring_equals_model_definition():
+    """oracle/plda_oracle.py restates the published fast PLDA scoring (parity with SpeechBrain unpinned).  What can be pinned:
+    its score equals the log-likelihood ratio of the two-covariance model evaluated straight from the Gaussian densities,
+    constant included, and the per-trial form equals the N x N matrix form."""
+    from oracle import plda_oracle as po
+    mean, F, S = po.synth_plda(32, 8, seed=1)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((9, 32)) + mean
+    sm = po.fast_plda_scoring(x[:4], x[4:], mean, F, S, scaling_factor=1.0)
+    direct = np.array([[po.llr_direct(e, t, mean, F, S) for t in x[4:]] for e in x[:4]])
+    assert np.abs(sm - direct).max() < 1e-10
+    e, t = np.array([0, 1, 3, 2]), np.array([4, 8, 5, 5])
+    assert np.abs(po.trial_scores(x, e, t, mean, F, S, 0.7) - 0.7 * sm[e, t - 4]).max() < 1e-12
+    # same-speaker pairs of the generative model score higher than different-speaker pairs on average
+    y = rng.standard_normal((200, 8))
+    L = np.linalg.cholesky(S)
+    a = mean + y @ F.T + rng.standard_normal((200, 32)) @ L.T
+    b = mean + y @ F.T + rng.standard_normal((200, 32)) @ L.T
+    same = po.trial_scores(np.vstack([a, b]), np.arange(200), 200 + np.arange(200), mean, F, S)
+    diff = po.trial_scores(np.vstack([a, b]), np.arange(200), 200 + np.roll(np.arange(200), 1), mean, F, S)
+    assert same.mean() > diff.mean() + 1.0
