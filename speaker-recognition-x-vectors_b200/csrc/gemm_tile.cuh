@@ -124,6 +124,18 @@ __device__ __forceinline__ void pool_epilogue_tile_t(const PoolArgs& p, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// L2 promotion of the TMA loads (XVEC_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B; developer A/B switch).  Measured on the stack
+// kernel: none / 64 B / 128 B 302.8 us, 256 B 305.5 us — every box row is one 128-byte line, 256 B promotion fetches a neighbour
+// line another CTA may not want yet.
+inline CUtensorMapL2promotion l2_promotion() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("XVEC_L2PROMO");
+    v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
+  }
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+       : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
 // 2-D row-major tensor map with 128-byte swizzle (the inner box is one 128-byte chunk).
 inline int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                         uint32_t box_inner, uint32_t box_outer) {
@@ -138,7 +150,7 @@ inline int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t i
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dtype == XVEC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(XVEC_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
   return XVEC_OK;
 }
