@@ -136,9 +136,9 @@ inline CUtensorMapL2promotion l2_promotion() {
   return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
        : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 }
-// 2-D row-major tensor map with 128-byte swizzle (the inner box is one 128-byte chunk).
+// 2-D row-major tensor map; the inner box is one swizzle-width chunk (128 bytes unless stated).
 inline int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                        uint32_t box_inner, uint32_t box_outer) {
+                        uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return set_error(XVEC_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const uint64_t es = dtype == XVEC_BF16 ? 2 : 4;
@@ -150,7 +150,7 @@ inline int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t i
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dtype == XVEC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(XVEC_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
   return XVEC_OK;
 }

@@ -379,10 +379,12 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     const int cbeg = ((warp - 2) >> 2) * (BN / 2);  // this warp's half of the tile's columns
     const int cend = cbeg + BN / 2;
     uint8_t* out_stage = epi_smem + (warp - 2) * (STACK_OUT_BUFS * OUT_BUF_BYTES);
-    constexpr int OUT_ES = kAllTf32 ? 4 : 2;
-    constexpr int GROUP_COLS = 128 / OUT_ES;         // columns per TMA-store box (128 bytes per row)
-    constexpr int CHUNKS = GROUP_COLS / 32;          // tcgen05.ld chunks per box
-    constexpr int BOXES = (BN / 2) / GROUP_COLS;     // boxes (= bulk groups) per tile and warp
+    // Store staging: one TMA-store box per tcgen05.ld chunk (32 rows x 32 columns).  bf16: 64-byte rows (SWIZZLE_64B), the warp's
+    // 4 KiB hold two boxes, so staging chunk k+1 overlaps the store of chunk k; float32: 128-byte rows, one box.
+    constexpr int BOX_W = kAllTf32 ? 128 : 64;                              // bytes per box row
+    constexpr int BOX_BYTES = 32 * BOX_W;
+    constexpr int NBUF = (STACK_OUT_BUFS * OUT_BUF_BYTES) / BOX_BYTES;      // boxes in flight per warp
+    constexpr int BOXES = (BN / 2) / 32;                                    // boxes (= bulk groups) per tile and warp
     int store_seq = 0;
     unsigned* pend = nullptr;  // ready counter of the last stored tile whose completion has not been published yet (warp-uniform)
     // Publish `pend`: lane 0 owns the warp's bulk groups; once they are complete the tile's rows are in global memory.
@@ -432,24 +434,18 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         if (pend) flush();  // its stores were issued a whole tile ago
       } else {
         const CUtensorMap* my = &maps.y[layer];
-        // tcgen05.ld of chunk k+1 is in flight while chunk k is converted and staged
-        constexpr int NCH = BOXES * CHUNKS;
+        // tcgen05.ld of chunk k+1 is in flight while chunk k is converted, staged and stored
         uint32_t va[32], vb[32];
         tmem_ld_32x32(tbase + cbeg, va);
         tmem_ld_wait();
-        uint8_t* ob = nullptr;
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-          const int bx = k / CHUNKS, cc = k % CHUNKS;
-          const int c = cbeg + bx * GROUP_COLS;
+        for (int k = 0; k < BOXES; ++k) {
           uint32_t(&v)[32] = (k & 1) ? vb : va;
-          if (k + 1 < NCH) tmem_ld_32x32(tbase + cbeg + 32 * (k + 1), (k & 1) ? va : vb);
-          if (cc == 0) {
-            ob = out_stage + (store_seq % STACK_OUT_BUFS) * OUT_BUF_BYTES;
-            if (lane == 0) tma_store_wait_read<STACK_OUT_BUFS - 1>();  // the store that last used this box has read it
-            __syncwarp();
-          }
-          const int col0 = n0 + c + cc * 32;
+          if (k + 1 < BOXES) tmem_ld_32x32(tbase + cbeg + 32 * (k + 1), (k & 1) ? va : vb);
+          uint8_t* ob = out_stage + (store_seq % NBUF) * BOX_BYTES;
+          if (lane == 0) tma_store_wait_read<NBUF - 1>();  // the store that last used this box has read it
+          __syncwarp();
+          const int col0 = n0 + cbeg + k * 32;
           // r = relu(acc + bias') — every BatchNorm is folded forward into the next layer's weights (xvector.py)
           float o[32];
           const float4* bp = reinterpret_cast<const float4*>(L.bias + col0);
@@ -460,9 +456,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
             const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), make_float2(bb.z, bb.w));
             o[j4 + 0] = a.x; o[j4 + 1] = a.y; o[j4 + 2] = d.x; o[j4 + 3] = d.y;
           }
-          // row `lane` of the box, 16-byte pieces XOR-swizzled like CU_TENSOR_MAP_SWIZZLE_128B expects
-          uint8_t* orow = ob + lane * 128;
-          if constexpr (!kAllTf32) {
+          // row `lane` of the box, 16-byte pieces XOR-swizzled like the tensor map's swizzle mode expects
+          uint8_t* orow = ob + lane * BOX_W;
+          if constexpr (!kAllTf32) {  // SWIZZLE_64B: piece index ^ address bits [7,9) = (row / 2) % 4
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 w;
@@ -470,27 +466,24 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
               w.y = pack_bf16x2_relu(o[8 * j + 2], o[8 * j + 3]);
               w.z = pack_bf16x2_relu(o[8 * j + 4], o[8 * j + 5]);
               w.w = pack_bf16x2_relu(o[8 * j + 6], o[8 * j + 7]);
-              const int piece = cc * 4 + j;
-              *reinterpret_cast<uint4*>(orow + ((piece ^ (lane & 7)) << 4)) = w;
+              *reinterpret_cast<uint4*>(orow + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
             }
-          } else {
+          } else {                    // SWIZZLE_128B: piece index ^ address bits [7,10) = row % 8
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 w = make_float4(fmaxf(o[4 * j], 0.f), fmaxf(o[4 * j + 1], 0.f), fmaxf(o[4 * j + 2], 0.f), fmaxf(o[4 * j + 3], 0.f));
               *reinterpret_cast<float4*>(orow + ((j ^ (lane & 7)) << 4)) = w;
             }
           }
-          if (k + 1 < NCH) tmem_ld_wait();
-          if (k == NCH - 2) release_tmem();  // the last tcgen05.ld of the tile has landed
-          if (cc == CHUNKS - 1) {
-            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-            __syncwarp();
-            if (lane == 0) {
-              if (row0 < p.rows) tma_store_2d(my, ob, n0 + c, row0, p.pol_y);  // rows past the matrix are clipped
-              tma_store_commit();  // one group per box, also when nothing was stored, so that the group arithmetic below holds
-            }
-            ++store_seq;
+          if (k + 1 < BOXES) tmem_ld_wait();
+          if (k == BOXES - 2) release_tmem();  // the last tcgen05.ld of the tile has landed
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            if (row0 < p.rows) tma_store_2d(my, ob, col0, row0, p.pol_y);  // rows past the matrix are clipped
+            tma_store_commit();  // one group per box, also when nothing was stored, so that the group arithmetic below holds
           }
+          ++store_seq;
         }
         if (pend) {  // the previous stored tile's groups are older than this tile's BOXES groups
           if (lane == 0 && !XVEC_SDBG(p, 2)) {
@@ -635,8 +628,9 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const float* x, int64_
     rc = make_tmap_2d(&local_maps.b[l], d.w_packed_dev, d.dtype, bke, static_cast<uint64_t>(d.taps) * L.cpt * n_pad, bke, bke, BN_CTA);
     if (rc) return rc;
     if (l + 1 < n_tdnn) {
+      // store boxes: 32 rows x 32 columns (64-byte rows / SWIZZLE_64B for bf16, 128-byte rows / SWIZZLE_128B for float32)
       rc = make_tmap_2d(&local_maps.y[l], act[l & 1], act_dtype, static_cast<uint64_t>(d.n), static_cast<uint64_t>(rows),
-                        static_cast<uint64_t>(act_ld), static_cast<uint32_t>(128 / (act_dtype == XVEC_BF16 ? 2 : 4)), 32);
+                        static_cast<uint64_t>(act_ld), 32, 32, act_dtype == XVEC_BF16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
       h = act[l & 1];
       h_ld = act_ld;
