@@ -159,12 +159,16 @@ typedef struct XvecLayerDesc {
  * 256-channel tile) is a work item drawn in order from a global counter by the CTA pairs; a tile of layer l+1 starts as soon as
  * the tiles of layer l it reads are complete (per-tile flags in ctrl_dev), so the layers overlap inside the launch.
  * replaces: time_context_layers (main.py:38-44) applied by extract_x_vec (main.py:82) + the reads of stat_pool (main.py:59-63).
- *   tdnn_host[0].dtype must be XVEC_F32 (the MFCCs); layers 1.. share one dtype (the activation dtype); layers 0..n-2 need
- *   n % XVEC_TILE_N == 0 and a bias; eval-mode BatchNorm folded forward as for xvec_extract_forward.
+ *   x_dev is of tdnn_host[0].dtype; layers 1.. share one dtype (the activation dtype); layers 0..n-2 need n % XVEC_TILE_N == 0
+ *   and a bias; eval-mode BatchNorm folded forward as for xvec_extract_forward.
+ *   Window form of a layer with consecutive taps (context [-2..2] of TDNN1, tdnn_layer.py:43-60): when its input rows are
+ *   dense (x_ld == channels) the taps*channels window of output row r is ONE contiguous run starting at row r, so the layer
+ *   may be described as taps = 1, cin = taps*channels with the real row stride x_ld = channels (rows overlap; the natural
+ *   nn.Linear weight is already in window order).  x_dev must then stay readable (finite values) for taps - 1 rows past `rows`.
  *   ctrl_dev: 128-byte aligned scratch of xvec_stack_ctrl_bytes(rows, n_tdnn) bytes, private to this call until it completes
  *   (the call zeroes it on `stream`).  Returns XVEC_E_ARG for stacks outside these limits (use the per-layer calls). */
 XVEC_API int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn);
-XVEC_API int xvec_tdnn_stack(const struct XvecLayerDesc* tdnn_host, int n_tdnn, const float* x_dev, int64_t rows, int64_t x_ld,
+XVEC_API int xvec_tdnn_stack(const struct XvecLayerDesc* tdnn_host, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld,
                     void* act0_dev, void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev,
                     float* part_dev, void* ctrl_dev, int64_t ctrl_bytes, void* stream);
 
@@ -175,13 +179,13 @@ XVEC_API int xvec_tdnn_stack(const struct XvecLayerDesc* tdnn_host, int n_tdnn, 
  * replaces: XVectorModel.extract_x_vec (main.py:81-94) = time_context_layers (main.py:38-44) + stat_pool (:59-63) +
  * segment_layer6 [+ relu + segment_layer7]; eval-mode BatchNorm of layers 0..n-2 must already be folded into the next
  * layer's packed weights, the last TDNN layer's BatchNorm is passed as bn_last_scale/shift (or NULL).
- *   x_dev (rows, tdnn[0].cin) float32, row stride x_ld;  act0/act1: ping-pong activation buffers (rows, act_ld) of the
+ *   x_dev (rows, tdnn[0].cin) of tdnn[0].dtype, row stride x_ld (window form: see xvec_tdnn_stack);  act0/act1: ping-pong activation buffers (rows, act_ld) of the
  *   dtype of tdnn[1];  layout arrays as for xvec_tdnn_pool_fused / xvec_pool_finalize;  part_dev (n_slots, 2, n_last);
  *   pooled_dev float32 (n_utts, 2 n_last);  pooled_lp_dev same in fc[0].dtype when that is XVEC_BF16, else NULL;
  *   fc_tmp_dev (n_utts, fc[0].n) of fc[1].dtype when n_fc == 2;  out_dev float32 (n_utts, fc[n_fc-1].n), row stride out_ld;
  *   splitk_ws_dev: scratch for the segment layers (see xvec_splitk_workspace_bytes) or NULL;
  *   ctrl_dev / ctrl_bytes: scratch of xvec_tdnn_stack or NULL / 0. */
-XVEC_API int xvec_extract_forward(const XvecLayerDesc* tdnn_host, int n_tdnn, const float* x_dev, int64_t rows, int64_t x_ld,
+XVEC_API int xvec_extract_forward(const XvecLayerDesc* tdnn_host, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld,
                          void* act0_dev, void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev,
                          const int32_t* blk_slot_base_dev, const int32_t* utt_slot_start_dev, const int32_t* n_pool_dev,
                          int n_utts, float* part_dev, const float* bn_last_scale_dev, const float* bn_last_shift_dev,

@@ -122,7 +122,7 @@ int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin
 
 int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn) { return stack_ctrl_bytes(rows, n_tdnn); }
 
-int xvec_tdnn_stack(const XvecLayerDesc* tdnn, int n_tdnn, const float* x_dev, int64_t rows, int64_t x_ld, void* act0_dev, void* act1_dev,
+int xvec_tdnn_stack(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld, void* act0_dev, void* act1_dev,
                     int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev, float* part_dev, void* ctrl_dev,
                     int64_t ctrl_bytes, void* stream) {
   if (!tdnn) return set_error(XVEC_E_ARG, "tdnn_host is NULL");
@@ -130,7 +130,7 @@ int xvec_tdnn_stack(const XvecLayerDesc* tdnn, int n_tdnn, const float* x_dev, i
                         ctrl_bytes, stream);
 }
 
-int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const float* x_dev, int64_t rows, int64_t x_ld, void* act0_dev,
+int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld, void* act0_dev,
                          void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev,
                          const int32_t* utt_slot_start_dev, const int32_t* n_pool_dev, int n_utts, float* part_dev,
                          const float* bn_last_scale_dev, const float* bn_last_shift_dev, float* pooled_dev, void* pooled_lp_dev,

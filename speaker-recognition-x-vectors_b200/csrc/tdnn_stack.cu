@@ -564,7 +564,7 @@ static int launch_stack(const StackMaps& maps, const StackParams& p, int grid, c
 
 bool stack_supported(const XvecLayerDesc* tdnn, int n_tdnn, int64_t rows) {
   if (n_tdnn < 2 || n_tdnn > XVEC_MAX_STACK || rows <= 0 || rows > 0x7fffff00LL) return false;
-  if (tdnn[0].dtype != XVEC_F32) return false;
+  if (tdnn[0].dtype != XVEC_F32 && tdnn[0].dtype != XVEC_BF16) return false;
   for (int i = 0; i < n_tdnn; ++i) {
     if (tdnn[i].taps < 1 || tdnn[i].taps > XVEC_MAX_TAPS) return false;
     if (i > 0 && (tdnn[i].dtype != tdnn[1].dtype || tdnn[i].cin != tdnn[i - 1].n)) return false;
@@ -580,7 +580,7 @@ bool stack_supported(const XvecLayerDesc* tdnn, int n_tdnn, int64_t rows) {
   return true;
 }
 
-int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const float* x, int64_t rows, int64_t x_ld, void* act0, void* act1,
+int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t rows, int64_t x_ld, void* act0, void* act1,
                    int64_t act_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part, void* ctrl, int64_t ctrl_bytes,
                    void* stream) {
   int rc = device_check();
@@ -599,7 +599,7 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const float* x, int64_
   void* act[2] = {act0, act1};
   const void* h = x;
   int64_t h_ld = x_ld;
-  int h_dtype = XVEC_F32;
+  int h_dtype = tdnn[0].dtype;
   int64_t items_per_mtile = 0;
   for (int l = 0; l < n_tdnn; ++l) {
     const XvecLayerDesc& d = tdnn[l];

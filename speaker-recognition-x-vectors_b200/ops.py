@@ -108,16 +108,16 @@ def tdnn_pool_fused(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
 
 
 def tdnn_stack(layer_descs, n_layers: int, x: torch.Tensor, act0: torch.Tensor, act1: torch.Tensor, row_utt: torch.Tensor,
-               blk_slot_base: torch.Tensor, part: torch.Tensor, ctrl: torch.Tensor):
+               blk_slot_base: torch.Tensor, part: torch.Tensor, ctrl: torch.Tensor, rows: int | None = None):
     """All TDNN layers of the stack in one persistent launch (xvec_tdnn_stack): layers 0..n-2 ping-pong through act0/act1,
     the last one fills the pooling partials `part`.  layer_descs: ctypes array of _lib.LayerDesc (packed operands)."""
     _require_cuda(x, act0, act1, row_utt, blk_slot_base, part, ctrl)
     lib = _lib.load()
     x_ld = _rowmajor_2d(x, "x")
     act_ld = _rowmajor_2d(act0, "act0")
-    rows = x.shape[0]
-    if x.dtype != torch.float32 or act0.dtype != act1.dtype or _rowmajor_2d(act1, "act1") != act_ld:
-        raise ValueError("x must be float32; act0 / act1 must share dtype and row stride")
+    rows = x.shape[0] if rows is None else rows  # window form of layer 0: x carries padding rows past `rows`
+    if dtype_code(x.dtype) != layer_descs[0].dtype or act0.dtype != act1.dtype or _rowmajor_2d(act1, "act1") != act_ld:
+        raise ValueError("x must have the dtype of layer 0; act0 / act1 must share dtype and row stride")
     if act0.shape[0] < rows or act1.shape[0] < rows:
         raise ValueError("activation buffers are too small for this frame matrix")
     if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * (256 // _lib.POOL_BLOCK) or not part.is_contiguous():

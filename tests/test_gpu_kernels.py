@@ -218,11 +218,17 @@ def test_stack_kernel_equals_per_layer_launches(xb, state_dict, precision, band,
     layers = list(m.time_context_layers)
     sc = m._scratch_for(0)
     sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
+    xs, rows = m._stack_input(pipe, sc, flat)
     h = flat
     acts = []
     for i, layer in enumerate(layers[:-1]):
         w, bias, offs = stack[i]
-        h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True, out_dtype=m.act_dtype, cin=layer.input_size)
+        if i == 0 and pipe["window"] is not None:
+            # bf16 pipeline: TDNN1 in window form — one K = 120 GEMM over overlapping rows of the bf16 copy of the frames
+            view = torch.as_strided(xs, (rows, 5 * 24), (24, 1))
+            h = ops.tdnn_layer_flat(view, pipe["window"]["w"], 512, [0], bias, None, None, relu=True, out_dtype=m.act_dtype, cin=120)
+        else:
+            h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True, out_dtype=m.act_dtype, cin=layer.input_size)
         acts.append(h)
     w, bias, offs = stack[-1]
     part_ref = torch.zeros((lay.n_slots, 2, 1500), device="cuda")
@@ -232,7 +238,7 @@ def test_stack_kernel_equals_per_layer_launches(xb, state_dict, precision, band,
     for rep in range(3):  # repeated launches reuse (and re-zero) the same control block
         part = torch.zeros((lay.n_slots, 2, 1500), device="cuda")
         sc.act[0].zero_(); sc.act[1].zero_()
-        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], flat, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, rows=rows)
         torch.cuda.synchronize()
         assert torch.equal(part, part_ref)
         # layer 3 / layer 4 outputs are what is left in the ping-pong buffers
