@@ -245,3 +245,38 @@ def test_stack_kernel_equals_per_layer_launches(xb, state_dict, precision, band,
         assert torch.equal(sc.act[0][: lay.rows, :512], acts[2])
         assert torch.equal(sc.act[1][: lay.rows, :512], acts[3])
     assert xb._lib.load().xvec_watchdog_code() == 0
+
+
+def test_stack_kernel_two_launches_in_flight(xb, state_dict, monkeypatch):
+    """Two tdnn_stack_kernel launches on two streams (separate scratch, dynamic tile queues) cannot starve or corrupt each other:
+    every result equals the single-launch result bit for bit (tools/stack_stress.py is the long version)."""
+    from xvec_b200 import ops
+    from oracle import xvector_oracle as ox
+    m = xb.XVectorModel(precision="bf16")
+    m.load_state_dict(state_dict)
+    m = m.cuda().eval()
+    lens = np.random.default_rng(3).integers(15, 900, size=90)
+    flat = torch.cat(ox.synth_ragged(lens, seed=8)).cuda()
+    lay = m._layout_for(lens)
+    pipe = m._pipeline()
+    scs = [m._scratch_for(s) for s in range(2)]
+    for sc in scs:
+        sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
+    xs = [m._stack_input(pipe, sc, flat) for sc in scs]
+    ref = torch.zeros((lay.n_slots, 2, 1500), device="cuda")
+    ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs[0][0], scs[0].act[0], scs[0].act[1], lay.row_utt, lay.blk_slot_base, ref, scs[0].ctrl,
+                   rows=xs[0][1])
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    for band in (0, 7):
+        if band:
+            monkeypatch.setenv("XVEC_BAND", str(band))
+        parts = [[torch.zeros_like(ref) for _ in range(4)] for _ in range(2)]
+        for rep in range(4):
+            for s in range(2):
+                with torch.cuda.stream(streams[s]):
+                    ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs[s][0], scs[s].act[0], scs[s].act[1], lay.row_utt, lay.blk_slot_base,
+                                   parts[s][rep], scs[s].ctrl, rows=xs[s][1])
+        torch.cuda.synchronize()
+        assert all(torch.equal(pt, ref) for ps in parts for pt in ps)
+    assert xb._lib.load().xvec_watchdog_code() == 0
