@@ -10,8 +10,8 @@
 //     drawn strictly in order and an item only depends on EARLIER items, so any number of resident CTAs makes progress —
 //     two of these kernels on two streams cannot deadlock each other.
 //   * item order: bands of `band` m-tiles; inside a band layer 1, 2, ... L, the m-range of layer l skewed down by l tiles
-//     (layer l+1 tile m reads layer l tiles m-1.. m+1, all in the same or an earlier band).  A band's activations
-//     (band*256 rows x 512 ch) stay in L2 between the layers; short-K / store-bound layers overlap with MMA-bound ones.
+//     (layer l+1 tile m reads layer l tiles m-1.. m+1, all in the same or an earlier band).  Bands must be long — producers
+//     run 3-4 tiles ahead of the published completions (see pick_band) — so a short batch is one band = layer after layer.
 //   * inter-layer dependencies: every epilogue warp adds 1 to ready[layer][m_tile] (red.release.gpu) once its TMA stores of
 //     that tile are COMPLETE (cp.async.bulk.wait_group, deferred so that it never blocks a busy warp); a dependency warp per
 //     CTA runs ahead of the TMA producer, polls (ld.acquire.gpu) the flags of the tiles the next items touch and hands each
@@ -19,9 +19,10 @@
 //     The two ping-pong activation buffers are safe: tile (l, m) overwrites rows whose readers (l-1, m-1) and (l-1, m) it
 //     has just waited for.
 //
-// The mainloop and TMEM double buffering are the ones of tdnn_gemm.cu; layer 1 always runs kind::tf32 on the float32 MFCCs, the
-// other layers kind::f16 (bf16) or kind::tf32 (kAllTf32).  The last layer is computed TRANSPOSED (weights as the M operand) so
-// that its pooling epilogue reduces over time in registers.
+// TMEM double buffering and the tcgen05 step are the ones of tdnn_gemm.cu.  Layers 1.. run kind::f16 (bf16) or kind::tf32
+// (kAllTf32); layer 0 runs in its own dtype: kind::tf32 on the float32 MFCCs, or kind::f16 on a bf16 copy of them in "window
+// form" (taps = 1, cin = taps*channels over overlapping rows; include/xvec_b200.h).  The last layer is computed TRANSPOSED
+// (weights as the M operand) so that its pooling epilogue reduces over time in registers.
 #include "gemm_tile.cuh"
 #include <cuda_bf16.h>
 
@@ -80,7 +81,7 @@ struct StackParams {
   unsigned band_first[XVEC_STACK_MAX_BANDS + 1];
 };
 
-// item -> (layer [0,3) | n_tile [3,8) | m_tile [8,32)).  Same arithmetic as stack_plan() on the host.
+// item -> (layer [0,3) | n_tile [3,8) | m_tile [8,32)).  stack_dispatch() builds band_first[] with the same band_layer_range().
 __host__ __device__ inline int band_layer_range(int band, int m_tiles, int b, int l, int* lo) {
   int a = b * band - l, z = (b + 1) * band - l;
   if (a < 0) a = 0;
@@ -103,10 +104,11 @@ __device__ __forceinline__ uint32_t decode_item(const StackParams& p, unsigned i
 
 // Developer switches (-DXVEC_DEBUG builds only; XVEC_STACK_DBG): 1 skip the dependency waits, 2 skip the completion
 // signalling (only together with 1), 4 skip the proxy fences (results are then undefined; timing experiments only).
-// Debug builds also accumulate counters in the spare words of the control block (ctrl[1..7], units of 64 cycles):
-// 1 tiles whose dependency warp had to spin on a flag, 2 flag polls, 3 cycles the producer waited for its dependency warp,
-// 4 cycles the scheduler waited to publish,
-// 5 cycles the MMA warp waited for operands, 6 cycles it waited for a free accumulator buffer, 7 cycles epilogue warp 2 waited for tfull.
+// Debug builds also accumulate counters in the spare words of the control block (read by tools/stack_bench.py; units of 64
+// cycles unless stated): 1 tiles whose dependency warp had to spin on a flag (count), 2 flag polls (count), 3 producer waiting
+// for its dependency warp, 4 producer waiting for the work item, 5 MMA warp waiting for operands (explicit waits only),
+// 6 MMA warp waiting for a free accumulator buffer, 8 / 9 lifetime of CTA 0 in cycles / nanoseconds (SM clock), 10 time inside
+// the tcgen05 step, 11 MMA warp waiting for the work item, 16.. / 24.. per layer: accumulator wait / whole tile (units of 16).
 #ifdef XVEC_DEBUG
 #define XVEC_SDBG(p, bit) ((p).dbg & (bit))
 #define XVEC_CNT(...) __VA_ARGS__
