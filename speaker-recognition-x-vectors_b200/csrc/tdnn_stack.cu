@@ -10,8 +10,9 @@
 //     drawn strictly in order and an item only depends on EARLIER items, so any number of resident CTAs makes progress —
 //     two of these kernels on two streams cannot deadlock each other.
 //   * item order: bands of `band` m-tiles; inside a band layer 1, 2, ... L, the m-range of layer l skewed down by l tiles
-//     (layer l+1 tile m reads layer l tiles m-1.. m+1, all in the same or an earlier band).  Bands must be long — producers
-//     run 3-4 tiles ahead of the published completions (see pick_band) — so a short batch is one band = layer after layer.
+//     (layer l+1 tile m reads layer l tiles m-1.. m+1, all in the same or an earlier band).  Bands of ~2.3 x pairs m-tiles are
+//     long enough that an item's inputs are complete when it is drawn and short enough that a band's activations stay in L2
+//     between the layers (see pick_band).
 //   * inter-layer dependencies: every epilogue warp adds 1 to ready[layer][m_tile] (red.release.gpu) once its TMA stores of
 //     that tile are COMPLETE (cp.async.bulk.wait_group, deferred so that it never blocks a busy warp); a dependency warp per
 //     CTA runs ahead of the TMA producer, polls (ld.acquire.gpu) the flags of the tiles the next items touch and hands each
@@ -517,14 +518,18 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// Band height.  Producers run 3-4 tiles ahead of the published completions, so an item's inputs are only certain to be
-// complete when they were drawn >= ~4 x pairs items earlier; measured on B200 (256 x 300 frames = 300 m-tiles): band 20 / 37 /
-// 74 / 148 / one band = 1.23 / 0.77 / 0.49 / 0.43 / 0.39 ms.  Hence bands of 8 x pairs m-tiles: short batches run layer after
-// layer, long ones keep >= 16 waves between a tile and its consumers.  XVEC_BAND overrides (developer A/B switch).
+// Band height.  Two opposing effects, both measured on B200 (256 x 300 frames = 300 m-tiles, bf16, 74 pairs):
+//   * producers run 3-4 tiles ahead of the published completions, so an item's inputs are only certain to be complete when they
+//     were drawn >= ~4 x pairs items earlier — bands of 100 / 148 m-tiles stall (364 us sustained, dependency warps spinning);
+//   * a band's activations (band x 128 KiB per layer and buffer) stay in L2 between the layers when the band is short enough,
+//     which saves the HBM round trip of every activation and the power that goes with it — the kernel runs at the 1000 W cap,
+//     so this is throughput: one band 294 / 336 us (burst / sustained), bands of 160-170: 278 / 322 us, 180-200: 282-284 /
+//     326-328 us, 225: 292 / 332 us, 250: 311 / 347 us.  64 x 6000 frames (1500 m-tiles): 1474 -> 1382 us; 437 x 300: 519 -> 467 us.
+// Hence bands of 2.3 x pairs m-tiles.  XVEC_BAND overrides (developer A/B switch).
 static int pick_band(int m_tiles, int n_layers, int pairs) {
   const char* e = getenv("XVEC_BAND");
   const int env = e ? atoi(e) : 0;
-  int band = env > 0 ? env : 8 * pairs;
+  int band = env > 0 ? env : (23 * pairs + 5) / 10;
   if (band < n_layers) band = n_layers;
   while ((m_tiles + n_layers - 1 + band - 1) / band > XVEC_STACK_MAX_BANDS) band *= 2;
   return band;
