@@ -16,13 +16,13 @@ LIB_PATH = os.environ.get("XVEC_LIB") or os.path.join(HERE, "libxvec_b200.so")  
 F32, BF16 = 0, 1
 E_ARG, E_CUDA, E_DEVICE = -1, -2, -3
 TILE_N, POOL_BLOCK, POOL_CHUNK, MAX_TAPS = 256, 128, 128, 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_STACK = 6
 
 class LayerDesc(ctypes.Structure):
     """XvecLayerDesc of include/xvec_b200.h."""
     _fields_ = [("w_packed_dev", c_void_p), ("bias_dev", c_void_p), ("n", c_int32), ("cin", c_int32), ("taps", c_int32),
-                ("dtype", c_int32), ("tap_offsets", c_int32 * MAX_TAPS)]
+                ("dtype", c_int32), ("tap_offsets", c_int32 * MAX_TAPS), ("w_plain_dev", c_void_p)]
 
 
 _SIGNATURES = {
@@ -48,6 +48,7 @@ _SIGNATURES = {
                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LayerDesc), c_int,
                                      c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "xvec_stack_ctrl_bytes": (c_int64, [c_int64, c_int]),
+    "xvec_linear_small": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
     "xvec_tdnn_stack": (c_int, [POINTER(LayerDesc), c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int64, c_void_p]),
     "xvec_mfcc_num_frames": (c_int64, [c_int64]),

@@ -76,6 +76,16 @@ static bool use_stack_kernel() {
   return v == 1;
 }
 
+// XVEC_FC_SMALL=0 keeps the segment layers on the tcgen05 kernel (developer A/B switch).
+static bool use_fc_small() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("XVEC_FC_SMALL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace xvec
 
 using namespace xvec;
@@ -121,6 +131,11 @@ int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin
 }
 
 int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn) { return stack_ctrl_bytes(rows, n_tdnn); }
+
+int xvec_linear_small(const void* x_dev, int64_t rows, int k, int64_t x_ld, const void* w_dev, int n, int64_t w_ld, const float* bias_dev,
+                      int relu, void* y_dev, int y_dtype, int64_t y_ld, void* stream) {
+  return fc_small_dispatch(x_dev, rows, k, x_ld, w_dev, n, w_ld, bias_dev, relu, y_dev, y_dtype, y_ld, stream);
+}
 
 int xvec_tdnn_stack(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld, void* act0_dev, void* act1_dev,
                     int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev, float* part_dev, void* ctrl_dev,
@@ -181,6 +196,16 @@ int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_de
     void* y = final_layer ? static_cast<void*>(out_dev) : fc_tmp_dev;
     const int y_dtype = final_layer ? XVEC_F32 : fc[i + 1].dtype;
     const int64_t y_ld = final_layer ? out_ld : fc[i].n;
+    if (fc[i].w_plain_dev && fc[i].dtype == XVEC_BF16 && use_fc_small() &&
+        fc_small_supported(n_utts, fc[i].cin, fc[i].n, a_ld, fc[i].cin, a, fc[i].w_plain_dev)) {
+      // small-footprint kernel: runs next to the resident stack CTAs of the next batch instead of waiting for free SMs
+      rc = fc_small_dispatch(a, n_utts, fc[i].cin, a_ld, fc[i].w_plain_dev, fc[i].n, fc[i].cin, fc[i].bias_dev, final_layer ? 0 : 1, y, y_dtype,
+                             y_ld, stream);
+      if (rc) return rc;
+      a = y;
+      a_ld = y_ld;
+      continue;
+    }
     rc = gemm_dispatch(a, fc[i].dtype, n_utts, fc[i].cin, a_ld, fc[i].w_packed_dev, fc[i].n, fc[i].tap_offsets, 1, fc[i].bias_dev, nullptr,
                        nullptr, final_layer ? 0 : 1, y, y_dtype, y_ld, nullptr, nullptr, nullptr, n_utts, false, splitk_ws_dev,
                        splitk_ws_bytes, stream);

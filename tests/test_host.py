@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib = xvec_b200._lib.load()
-    assert lib.xvec_abi_version() == xvec_b200._lib.ABI_VERSION == 3
+    assert lib.xvec_abi_version() == xvec_b200._lib.ABI_VERSION == 4
     assert lib.xvec_packed_k(24, 5, xvec_b200._lib.F32) == 160 and lib.xvec_packed_k(512, 3, xvec_b200._lib.BF16) == 1536
     assert lib.xvec_packed_k(3000, 1, xvec_b200._lib.BF16) == 3008 and lib.xvec_packed_n(1500) == 1536
 
