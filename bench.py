@@ -251,14 +251,13 @@ def run_b200(args, rank, world, local_rank):
                        "global_batch": BATCH * world, "frames": FRAMES, "parallelism": f"utterance-sharded x{world}, no data-path collective",
                        "l2": f"inputs larger than L2: {n_res} distinct device-resident batches ({n_res * BATCH * FRAMES * CEPS * 4 >> 20} MiB) cycled; "
                              "2 batches in flight, activations of the two (4 x 78 MB) also exceed the 126 MB L2",
-                       "tdnn1": ("bf16 window form: one K = 120 GEMM over overlapping rows of a bf16 copy of the frames (cast inside every step)"
-                                 if precision == "bf16" else "TF32 math on the float32 MFCCs")},
+                       "tdnn1": "TF32 math on the float32 MFCCs in both modes (window form: one K = 120 GEMM over overlapping rows)"},
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": hx.h2d_bytes // args.steps, "d2h_bytes_per_step": hx.d2h_bytes // args.steps,
                     "api": "HostExtractor.submit/result (pinned host MFCCs in, pinned host x-vectors out, 6 slots / streams)",
                     "frames_per_sec": e2e * FRAMES, "checksum": checksum},
-            # per step: [cast_kernel (bf16: frames -> bf16 for TDNN1's window form),] tdnn_stack_kernel, pool_finalize_kernel,
-            # tdnn_gemm_kernel (segment6, split-K), splitk_reduce_kernel
-            "gpu_launches": args.steps * (5 if precision == "bf16" else 4),
+            # per step: tdnn_stack_kernel, pool_finalize_kernel, then fc_small_kernel (bf16) or tdnn_gemm_kernel (segment6, split-K) +
+            # splitk_reduce_kernel (TF32)
+            "gpu_launches": args.steps * (3 if precision == "bf16" else 4),
             "clocks": clocks,
             "wall_ms_per_step": t_wall / args.steps * 1e3,
             "roofline": {"kernel": "tdnn_stack_kernel (1 launch/step: all tiles of TDNN1-5 from one work queue; TDNN5 epilogue = pooling partials)",
@@ -298,10 +297,10 @@ def instrumented_stack_time(model, x_dev, lengths, n_batches, iters):
     part = sc.part[: lay.n_slots]
     evs = []
     for it in range(iters + 3):
-        x, rows = model._stack_input(pipe, sc, x_dev[it % n_batches])  # bf16: the xvec_cast launch of the step, outside the bracket
+        x = _aligned_rows(x_dev[it % n_batches])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], x, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, rows=rows)
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], x, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()

@@ -166,7 +166,9 @@ typedef struct XvecLayerDesc {
  *   Window form of a layer with consecutive taps (context [-2..2] of TDNN1, tdnn_layer.py:43-60): when its input rows are
  *   dense (x_ld == channels) the taps*channels window of output row r is ONE contiguous run starting at row r, so the layer
  *   may be described as taps = 1, cin = taps*channels with the real row stride x_ld = channels (rows overlap; the natural
- *   nn.Linear weight is already in window order).  x_dev must then stay readable (finite values) for taps - 1 rows past `rows`.
+ *   nn.Linear weight is already in window order).  Rows whose window would run past the end of x (the last taps - 1 rows, which
+ *   are don't-care rows of the last utterance anyway) read as zero; nothing past the end of x_dev is touched.
+ *   xvec_tdnn_layer / xvec_tdnn_pool_fused accept the same form.
  *   ctrl_dev: 128-byte aligned scratch of xvec_stack_ctrl_bytes(rows, n_tdnn) bytes, private to this call until it completes
  *   (the call zeroes it on `stream`).  Returns XVEC_E_ARG for stacks outside these limits (use the per-layer calls). */
 XVEC_API int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn);

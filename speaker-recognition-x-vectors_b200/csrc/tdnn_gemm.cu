@@ -540,7 +540,10 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
   }
 
   CUtensorMap ta, tb, ty;
-  rc = make_tmap_2d(&ta, x, x_dtype, static_cast<uint64_t>(cin), static_cast<uint64_t>(x_rows), static_cast<uint64_t>(x_ld), bke, BM_CTA);
+  // window form (x_ld < cin: overlapping rows): only rows whose whole window lies inside the matrix exist, the rest read as zero
+  const int64_t a_rows = x_ld < cin ? x_rows - (cin + x_ld - 1) / x_ld + 1 : x_rows;
+  if (a_rows <= 0) return set_error(XVEC_E_ARG, "window form: fewer rows than one window");
+  rc = make_tmap_2d(&ta, x, x_dtype, static_cast<uint64_t>(cin), static_cast<uint64_t>(a_rows), static_cast<uint64_t>(x_ld), bke, BM_CTA);
   if (rc) return rc;
   // packed weights are chunk-major (xvec_pack_weight): a (kblocks * n_pad) x bke matrix, one contiguous 16 KiB box per load
   rc = make_tmap_2d(&tb, w_packed, x_dtype, bke, static_cast<uint64_t>(taps) * p.cpt * p.n_tiles * BN, bke, bke, BN_CTA);

@@ -626,7 +626,10 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
     L.bias = d.bias_dev;
     if (reinterpret_cast<uintptr_t>(d.bias_dev) & 15u) return set_error(XVEC_E_ARG, "bias must be 16-byte aligned");
     items_per_mtile += L.n_tiles;
-    rc = make_tmap_2d(&local_maps.a[l], h, h_dtype, static_cast<uint64_t>(d.cin), static_cast<uint64_t>(rows), static_cast<uint64_t>(h_ld),
+    // window form (h_ld < cin: overlapping rows): only rows whose whole window lies inside the matrix exist, the rest read as zero
+    const int64_t h_rows = h_ld < d.cin ? rows - (d.cin + h_ld - 1) / h_ld + 1 : rows;
+    if (h_rows <= 0) return set_error(XVEC_E_ARG, "window form: fewer rows than one window");
+    rc = make_tmap_2d(&local_maps.a[l], h, h_dtype, static_cast<uint64_t>(d.cin), static_cast<uint64_t>(h_rows), static_cast<uint64_t>(h_ld),
                       bke, static_cast<uint32_t>(L.slab_rows));
     if (rc) return rc;
     // packed weights are chunk-major (xvec_pack_weight): a (kblocks * n_pad) x bke matrix, one contiguous 16 KiB box per load

@@ -108,14 +108,14 @@ def tdnn_pool_fused(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
 
 
 def tdnn_stack(layer_descs, n_layers: int, x: torch.Tensor, act0: torch.Tensor, act1: torch.Tensor, row_utt: torch.Tensor,
-               blk_slot_base: torch.Tensor, part: torch.Tensor, ctrl: torch.Tensor, rows: int | None = None):
+               blk_slot_base: torch.Tensor, part: torch.Tensor, ctrl: torch.Tensor):
     """All TDNN layers of the stack in one persistent launch (xvec_tdnn_stack): layers 0..n-2 ping-pong through act0/act1,
     the last one fills the pooling partials `part`.  layer_descs: ctypes array of _lib.LayerDesc (packed operands)."""
     _require_cuda(x, act0, act1, row_utt, blk_slot_base, part, ctrl)
     lib = _lib.load()
     x_ld = _rowmajor_2d(x, "x")
     act_ld = _rowmajor_2d(act0, "act0")
-    rows = x.shape[0] if rows is None else rows  # window form of layer 0: x carries padding rows past `rows`
+    rows = x.shape[0]
     if dtype_code(x.dtype) != layer_descs[0].dtype or act0.dtype != act1.dtype or _rowmajor_2d(act1, "act1") != act_ld:
         raise ValueError("x must have the dtype of layer 0; act0 / act1 must share dtype and row stride")
     if act0.shape[0] < rows or act1.shape[0] < rows:

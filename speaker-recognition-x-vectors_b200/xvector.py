@@ -79,7 +79,7 @@ class _Scratch:
         per16 = 16 // torch.empty((), dtype=act_dtype).element_size()
         self.ld = (max(widths) + per16 - 1) // per16 * per16
         self.rows_cap = self.slots_cap = self.utts_cap = 0
-        self.act = self.part = self.pooled = self.pooled_lp = self.ctrl = self.x_lp = None
+        self.act = self.part = self.pooled = self.pooled_lp = self.ctrl = None
         self.fc_tmp = self.ws = None
         self.ws_for = None
 
@@ -92,7 +92,6 @@ class _Scratch:
             self.ctrl = torch.empty(need + 128, dtype=torch.uint8, device=self.device)
             off = (-self.ctrl.data_ptr()) % 128
             self.ctrl = self.ctrl[off: off + need]
-            self.x_lp = None
         if n_slots > self.slots_cap:
             self.slots_cap = max(n_slots, int(self.slots_cap * 1.25))
             self.part = torch.empty((self.slots_cap, 2, self.pool_dim), dtype=torch.float32, device=self.device)
@@ -102,12 +101,6 @@ class _Scratch:
             self.pooled_lp = (torch.empty((self.utts_cap, 2 * self.pool_dim), dtype=self.act_dtype, device=self.device)
                               if self.act_dtype != torch.float32 else None)
             self.fc_tmp = None
-
-    def ensure_x_lp(self, channels: int, pad_rows: int):
-        """bf16 copy of the input frames for the window form of TDNN1 (+ pad_rows readable rows past the end)."""
-        if self.x_lp is None or self.x_lp.shape[1] != channels or self.x_lp.shape[0] < self.rows_cap + pad_rows:
-            self.x_lp = torch.zeros((self.rows_cap + pad_rows, channels), dtype=self.act_dtype, device=self.device)
-        return self.x_lp
 
     def ensure_head(self, n_utts, fc_shapes, width):
         """Scratch of the segment layers: the hidden (n_utts, width) activation and the split-K workspace."""
@@ -204,7 +197,7 @@ class XVectorModel(nn.Module):
             W'_i = W_i . diag(s_{i-1} (x) 1_k),   b'_i = b_i + W_i . (h_{i-1} (x) 1_k)
         so each epilogue is just relu(acc + b'); the last layer's BN is folded through the statistics by
         xvec_pool_finalize (mean' = s.mean + h, std' = |s|.std).  Computed once in float64, cached until parameters change.
-        Layer 1 is packed here for the float32 MFCCs (TF32 math); the bf16 pipeline replaces it by its window form (_pipeline)."""
+        Layer 1 reads the float32 MFCCs (TF32 math) in both precisions; the fused pipeline uses its window form (_pipeline)."""
         layers = list(self.time_context_layers)
         fp = tuple(l._fingerprint() for l in layers) + (self.precision,)
         hit = self._fc_prep.get("stack")
@@ -246,13 +239,13 @@ class XVectorModel(nn.Module):
         for i, (layer, (w, bias, offs)) in enumerate(zip(layers, stack)):
             d = tdnn[i]
             cin, taps = layer.input_size, len(offs)
-            if (i == 0 and self.act_dtype == torch.bfloat16 and list(offs) == list(range(taps)) and taps > 1
-                    and (cin * 2) % 16 == 0 and self._stack_kernel_ok()):
+            if i == 0 and list(offs) == list(range(taps)) and taps > 1 and (cin * 4) % 16 == 0 and self._stack_kernel_ok():
                 # Window form of TDNN1 (include/xvec_b200.h, xvec_tdnn_stack): consecutive taps over dense rows are one
-                # contiguous run of taps*cin values, so the layer is a plain K = 120 GEMM over overlapping rows of a bf16 copy
-                # of the frames: 2 K chunks per tile instead of 5 TF32 ones.  nn.Linear's weight is already in window order.
-                w = ops.pack_weight(layer.linear.weight.detach().float(), 1, taps * cin, torch.bfloat16)
-                window = {"w": w, "pad_rows": taps - 1, "channels": cin}
+                # contiguous run of taps*cin values, so the layer is a plain K = 120 GEMM over overlapping rows of the float32
+                # frames (TF32 math): 4 K chunks per tile instead of 5, no unfold, no copy.  nn.Linear's weight is already in
+                # window order.
+                w = ops.pack_weight(layer.linear.weight.detach().float(), 1, taps * cin, torch.float32)
+                window = {"w": w, "cin": taps * cin}
                 cin, offs = taps * cin, [0]
             d.w_packed_dev, d.bias_dev = w.data_ptr(), (bias.data_ptr() if bias is not None else None)
             d.n, d.cin, d.taps, d.dtype = layer.output_size, cin, len(offs), code(w.dtype)
@@ -296,17 +289,6 @@ class XVectorModel(nn.Module):
         return ops.tdnn_layer_flat(x2d, w, lin.out_features, [0], b, None, None, relu=relu, out_dtype=out_dtype, cin=lin.in_features,
                                    workspace=self._fc_prep[key])
 
-    def _stack_input(self, pipe, sc, flat_x: torch.Tensor):
-        """(tensor, rows) handed to the stack kernel: the float32 frames themselves, or — window form of TDNN1 — their bf16 copy
-        in the slot's padded scratch (one xvec_cast launch; replaces samples.float() of main.py:137 for the bf16 pipeline)."""
-        x = _aligned_rows(flat_x)
-        win = pipe["window"]
-        if win is None:
-            return x, x.shape[0]
-        x_lp = sc.ensure_x_lp(win["channels"], win["pad_rows"] + 4)
-        ops.cast(x, x_lp.dtype, out=x_lp[: x.shape[0]])
-        return x_lp, x.shape[0]
-
     # ------------------------------------------------------------------ the hot path
     def pooled_stats_flat(self, flat_x: torch.Tensor, lengths, slot: int = 0) -> "tuple[torch.Tensor, torch.Tensor | None]":
         """TDNN stack + statistics pooling over a flat (rows, input_size) float32 frame matrix.
@@ -329,10 +311,9 @@ class XVectorModel(nn.Module):
         part = sc.part[: lay.n_slots]
         pooled = sc.pooled[: lay.n_utts]
         pooled_lp = None if sc.pooled_lp is None else sc.pooled_lp[: lay.n_utts]
-        x = _aligned_rows(flat_x)
+        x = _aligned_rows(flat_x)  # layer 1 always reads the float32 frames (TF32 math): no cast pass over the input
         if self._stack_kernel_ok():
-            xs, rows = self._stack_input(pipe, sc, flat_x)
-            ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, rows=rows)
+            ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], x, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
         else:  # layer widths the one-launch stack kernel does not take: one launch per layer
             layers = list(self.time_context_layers)
             stack = pipe["keep"][0]
@@ -373,7 +354,7 @@ class XVectorModel(nn.Module):
         sc.ensure_head(lay.n_utts, pipe["fc_shapes"], pipe["hidden"])
         if flat_x.dtype != torch.float32:
             flat_x = flat_x.float()
-        x, _ = self._stack_input(pipe, sc, flat_x)
+        x = _aligned_rows(flat_x)
         out = torch.empty((lay.n_utts, pipe["out_dim"]), dtype=torch.float32, device=flat_x.device)
         lib = _lib.load()
         p = _lib.ptr

@@ -218,14 +218,14 @@ def test_stack_kernel_equals_per_layer_launches(xb, state_dict, precision, band,
     layers = list(m.time_context_layers)
     sc = m._scratch_for(0)
     sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
-    xs, rows = m._stack_input(pipe, sc, flat)
+    xs, rows = flat, flat.shape[0]
     h = flat
     acts = []
     for i, layer in enumerate(layers[:-1]):
         w, bias, offs = stack[i]
         if i == 0 and pipe["window"] is not None:
-            # bf16 pipeline: TDNN1 in window form — one K = 120 GEMM over overlapping rows of the bf16 copy of the frames
-            view = torch.as_strided(xs, (rows, 5 * 24), (24, 1))
+            # TDNN1 in window form — one K = 120 GEMM over overlapping rows of the frames (windows past the end read as zero)
+            view = torch.as_strided(torch.cat([xs, xs.new_zeros(4, 24)]), (rows, 5 * 24), (24, 1))  # storage must cover the nominal view
             h = ops.tdnn_layer_flat(view, pipe["window"]["w"], 512, [0], bias, None, None, relu=True, out_dtype=m.act_dtype, cin=120)
         else:
             h = ops.tdnn_layer_flat(h, w, layer.output_size, offs, bias, None, None, relu=True, out_dtype=m.act_dtype, cin=layer.input_size)
@@ -238,7 +238,7 @@ def test_stack_kernel_equals_per_layer_launches(xb, state_dict, precision, band,
     for rep in range(3):  # repeated launches reuse (and re-zero) the same control block
         part = torch.zeros((lay.n_slots, 2, 1500), device="cuda")
         sc.act[0].zero_(); sc.act[1].zero_()
-        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, rows=rows)
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
         torch.cuda.synchronize()
         assert torch.equal(part, part_ref)
         # layer 3 / layer 4 outputs are what is left in the ping-pong buffers
@@ -262,10 +262,9 @@ def test_stack_kernel_two_launches_in_flight(xb, state_dict, monkeypatch):
     scs = [m._scratch_for(s) for s in range(2)]
     for sc in scs:
         sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
-    xs = [m._stack_input(pipe, sc, flat) for sc in scs]
+    xs = [(flat, flat.shape[0]) for _ in scs]
     ref = torch.zeros((lay.n_slots, 2, 1500), device="cuda")
-    ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs[0][0], scs[0].act[0], scs[0].act[1], lay.row_utt, lay.blk_slot_base, ref, scs[0].ctrl,
-                   rows=xs[0][1])
+    ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs[0][0], scs[0].act[0], scs[0].act[1], lay.row_utt, lay.blk_slot_base, ref, scs[0].ctrl)
     torch.cuda.synchronize()
     streams = [torch.cuda.Stream() for _ in range(2)]
     for band in (0, 7):
@@ -276,7 +275,7 @@ def test_stack_kernel_two_launches_in_flight(xb, state_dict, monkeypatch):
             for s in range(2):
                 with torch.cuda.stream(streams[s]):
                     ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs[s][0], scs[s].act[0], scs[s].act[1], lay.row_utt, lay.blk_slot_base,
-                                   parts[s][rep], scs[s].ctrl, rows=xs[s][1])
+                                   parts[s][rep], scs[s].ctrl)
         torch.cuda.synchronize()
         assert all(torch.equal(pt, ref) for ps in parts for pt in ps)
     assert xb._lib.load().xvec_watchdog_code() == 0

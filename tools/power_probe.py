@@ -27,10 +27,10 @@ def sampler():
 def run(n):
     evs = []
     for it in range(n):
-        xs, rows = m._stack_input(pipe, sc, x[it % NRES])
+        xs = x[it % NRES]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, rows=rows)
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
         e1.record(); evs.append((e0, e1))
     torch.cuda.synchronize()
     return [a.elapsed_time(b) for a, b in evs]

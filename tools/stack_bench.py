@@ -40,10 +40,10 @@ flops = args.batch * sum(f * (args.frames - l) for f, l in zip([122880, 1572864,
 def run(iters):
     evs = []
     for it in range(iters + 3):
-        xs, rows = m._stack_input(pipe, sc, x[it % n_res])
+        xs = x[it % n_res]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, rows=rows)
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()

@@ -28,8 +28,8 @@ def step(i, split):
     part = sc.part[: lay.n_slots]; pooled = sc.pooled[: lay.n_utts]; pooled_lp = sc.pooled_lp[: lay.n_utts]
     with torch.cuda.stream(main[s]):
         if split: main[s].wait_event(evs[k][1])      # the tail that last read this scratch set is done
-        xs, rows = m._stack_input(pipe, sc, x[i % NRES])
-        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, rows=rows)
+        xs = x[i % NRES]
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
         if split: evs[k][0].record(main[s])
     with torch.cuda.stream(tail[s] if split else main[s]):
         if split: tail[s].wait_event(evs[k][0])
