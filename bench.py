@@ -376,7 +376,7 @@ def pooling_roofline(model, dev, peaks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)  # ~0.3 s per leg: long enough for the 1000 W power cap to engage
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
