@@ -3,7 +3,7 @@
 //   y[r, n] = epi( sum_{tap j} sum_{ch} x[r + off_j, ch] * W[n, j*Cin + ch] )
 //
 // replaces tdnn_layer.py:26-41 (get_time_context + torch.cat + nn.Linear + ReLU + eval BatchNorm1d) without ever
-// materialising the unfolded (rows x taps*Cin) tensor: the K loop runs over (tap, 128-byte channel chunk) and the
+// materialising the unfolded (rows x taps*Cin) tensor: the K loop runs over (128-byte channel chunk, tap) and the
 // TMA producer simply shifts the row coordinate of the A tile by the tap's frame offset.  Rows past the end of the
 // matrix and channels past Cin are zero-filled by TMA, the packed weights carry matching zero padding.
 //
@@ -17,12 +17,16 @@
 //   warp 1      TMEM owner; in the leader CTA it issues tcgen05.mma.cta_group::2 (UMMA 256x256xK, fp32 accumulators in
 //               TMEM, two 256-column buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
 //               Both run warp-uniform loops (addresses / descriptors stay in uniform registers) and predicate only the
-//               single-thread instructions on one elected lane; each step first probes the NEXT stage's barrier so the
-//               probe latency overlaps the TMA / MMA issue (ptx.cuh: tma_step_pair, umma_step_pair).
+//               single-thread instructions on one elected lane; each step ends with a probe of the NEXT stage's barrier
+//               (ptx.cuh: tma_step_pair, umma_step_pair).
 //   warps 2-9   epilogue (both CTAs, 128 rows each; 2 warps per TMEM lane quarter, each half of the columns):
 //               tcgen05.ld -> bias/ReLU (packed f32x2, cvt.relu) / BatchNorm affine -> 128B-swizzled smem staging
 //               -> TMA store                                                                  (EPI_STORE_*)
-//               or -> per-utterance column sums of r and r^2 (statistics pooling partials)    (EPI_POOL)
+//               or (tile computed TRANSPOSED: weights = M operand) -> per-utterance sums over time of r and r^2 in
+//               registers, statistics pooling partials (gemm_tile.cuh: pool_epilogue_tile_t)   (EPI_POOL)
+// The whole five-layer stack of the extraction path runs through tdnn_stack.cu instead (one persistent launch); this kernel
+// serves the segment layers of the TF32 pipeline (split-K), the standalone TdnnLayer module, the PLDA GEMMs and stacks the
+// fused kernel does not take.
 #include "gemm_tile.cuh"
 #include <cuda_bf16.h>
 
