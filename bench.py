@@ -257,9 +257,8 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": hx.h2d_bytes // args.steps, "d2h_bytes_per_step": hx.d2h_bytes // args.steps,
                     "api": "HostExtractor.submit/result (pinned host MFCCs in, pinned host x-vectors out, 6 slots / streams)",
                     "frames_per_sec": e2e * FRAMES, "checksum": checksum},
-            # per step: tdnn_stack_kernel, pool_finalize_kernel, then fc_small_kernel (bf16) or tdnn_gemm_kernel (segment6, split-K) +
-            # splitk_reduce_kernel (TF32)
-            "gpu_launches": args.steps * (3 if precision == "bf16" else 4),
+            # per step: tdnn_stack_kernel, pool_finalize_kernel, fc_small_kernel (segment6)
+            "gpu_launches": args.steps * 3,
             "clocks": clocks,
             "wall_ms_per_step": t_wall / args.steps * 1e3,
             "roofline": {"kernel": "tdnn_stack_kernel (1 launch/step: all tiles of TDNN1-5 from one work queue; TDNN5 epilogue = pooling partials)",

@@ -152,7 +152,7 @@ typedef struct XvecLayerDesc {
   int32_t taps;
   int32_t dtype;  /* XVEC_F32 / XVEC_BF16: element type of this layer's INPUT activations and packed weights */
   int32_t tap_offsets[XVEC_MAX_TAPS];
-  const void* w_plain_dev; /* segment layers only, optional: the nn.Linear weight itself as bfloat16 (n, cin) row-major, row
+  const void* w_plain_dev; /* segment layers only, optional: the nn.Linear weight itself in `dtype`, (n, cin) row-major, row
                               stride cin — lets xvec_extract_forward run the layer with xvec_linear_small; NULL otherwise */
 } XvecLayerDesc;
 
@@ -176,13 +176,13 @@ XVEC_API int xvec_tdnn_stack(const struct XvecLayerDesc* tdnn_host, int n_tdnn, 
                     void* act0_dev, void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev,
                     float* part_dev, void* ctrl_dev, int64_t ctrl_bytes, void* stream);
 
-/* Small-footprint linear layer: y = act(x W' + bias), x bfloat16 (rows, k), W bfloat16 (n, k) row-major (the nn.Linear layout,
- * NOT packed), float32 accumulation, y float32 or bfloat16.  128 threads, 5 KiB of shared memory, no tensor memory: its CTAs fit
- * next to a resident CTA of the persistent xvec_tdnn_stack kernel, so the segment layers of one batch run concurrently with the
- * frame-level stack of the next one instead of waiting for free SMs.
+/* Small-footprint linear layer: y = act(x W' + bias), x (rows, k) and W (n, k) row-major (the nn.Linear layout, NOT packed) of
+ * `dtype` (XVEC_BF16, or XVEC_F32 = TF32 math), float32 accumulation, y float32 or bfloat16.  128 threads, 5 KiB of shared
+ * memory, no tensor memory: its CTAs fit next to a resident CTA of the persistent xvec_tdnn_stack kernel, so the segment layers
+ * of one batch run concurrently with the frame-level stack of the next one instead of waiting for free SMs.
  * replaces: segment_layer6 / segment_layer7 (main.py:45-46, 87-90) on the pooled statistics.
- * k, x_ld, w_ld multiples of 8 elements; x_dev / w_dev 16-byte aligned; bias_dev float32 (n) or NULL. */
-XVEC_API int xvec_linear_small(const void* x_dev, int64_t rows, int k, int64_t x_ld, const void* w_dev, int n, int64_t w_ld,
+ * k, x_ld, w_ld multiples of 16 bytes of elements; x_dev / w_dev 16-byte aligned; bias_dev float32 (n) or NULL. */
+XVEC_API int xvec_linear_small(const void* x_dev, int dtype, int64_t rows, int k, int64_t x_ld, const void* w_dev, int n, int64_t w_ld,
                       const float* bias_dev, int relu, void* y_dev, int y_dtype, int64_t y_ld, void* stream);
 
 /* The whole extraction path for one flat batch in ONE call (4 kernel launches enqueued on `stream`, no host work besides

@@ -132,9 +132,9 @@ int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin
 
 int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn) { return stack_ctrl_bytes(rows, n_tdnn); }
 
-int xvec_linear_small(const void* x_dev, int64_t rows, int k, int64_t x_ld, const void* w_dev, int n, int64_t w_ld, const float* bias_dev,
-                      int relu, void* y_dev, int y_dtype, int64_t y_ld, void* stream) {
-  return fc_small_dispatch(x_dev, rows, k, x_ld, w_dev, n, w_ld, bias_dev, relu, y_dev, y_dtype, y_ld, stream);
+int xvec_linear_small(const void* x_dev, int dtype, int64_t rows, int k, int64_t x_ld, const void* w_dev, int n, int64_t w_ld,
+                      const float* bias_dev, int relu, void* y_dev, int y_dtype, int64_t y_ld, void* stream) {
+  return fc_small_dispatch(x_dev, dtype, rows, k, x_ld, w_dev, n, w_ld, bias_dev, relu, y_dev, y_dtype, y_ld, stream);
 }
 
 int xvec_tdnn_stack(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld, void* act0_dev, void* act1_dev,
@@ -196,11 +196,11 @@ int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_de
     void* y = final_layer ? static_cast<void*>(out_dev) : fc_tmp_dev;
     const int y_dtype = final_layer ? XVEC_F32 : fc[i + 1].dtype;
     const int64_t y_ld = final_layer ? out_ld : fc[i].n;
-    if (fc[i].w_plain_dev && fc[i].dtype == XVEC_BF16 && use_fc_small() &&
-        fc_small_supported(n_utts, fc[i].cin, fc[i].n, a_ld, fc[i].cin, a, fc[i].w_plain_dev)) {
+    if (fc[i].w_plain_dev && use_fc_small() &&
+        fc_small_supported(n_utts, fc[i].cin, fc[i].n, a_ld, fc[i].cin, a, fc[i].w_plain_dev, fc[i].dtype)) {
       // small-footprint kernel: runs next to the resident stack CTAs of the next batch instead of waiting for free SMs
-      rc = fc_small_dispatch(a, n_utts, fc[i].cin, a_ld, fc[i].w_plain_dev, fc[i].n, fc[i].cin, fc[i].bias_dev, final_layer ? 0 : 1, y, y_dtype,
-                             y_ld, stream);
+      rc = fc_small_dispatch(a, fc[i].dtype, n_utts, fc[i].cin, a_ld, fc[i].w_plain_dev, fc[i].n, fc[i].cin, fc[i].bias_dev,
+                             final_layer ? 0 : 1, y, y_dtype, y_ld, stream);
       if (rc) return rc;
       a = y;
       a_ld = y_ld;

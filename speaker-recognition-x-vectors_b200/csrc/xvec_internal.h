@@ -31,9 +31,9 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
                    int64_t act_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part, void* ctrl, int64_t ctrl_bytes,
                    void* stream);
 // fc_small.cu: small-footprint linear layer (mma.sync) that co-resides with the persistent stack kernel.
-bool fc_small_supported(int64_t rows, int k, int n, int64_t x_ld, int64_t w_ld, const void* x, const void* w);
-int fc_small_dispatch(const void* x, int64_t rows, int k, int64_t x_ld, const void* w, int n, int64_t w_ld, const float* bias, int relu,
-                      void* y, int y_dtype, int64_t y_ld, void* stream);
+bool fc_small_supported(int64_t rows, int k, int n, int64_t x_ld, int64_t w_ld, const void* x, const void* w, int dtype);
+int fc_small_dispatch(const void* x, int dtype, int64_t rows, int k, int64_t x_ld, const void* w, int n, int64_t w_ld, const float* bias,
+                      int relu, void* y, int y_dtype, int64_t y_ld, void* stream);
 int64_t splitk_workspace_bytes(int64_t rows, int cin, int taps, int n, int dtype);
 int read_watchdog();
 int read_trace(long long* out_host, int n);

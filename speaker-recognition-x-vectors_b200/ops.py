@@ -295,18 +295,18 @@ def plda_trials(xvecs: torch.Tensor, mean: torch.Tensor, w_phi: torch.Tensor, b_
 
 def linear_small(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, relu: bool = False,
                  out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """y = act(x W' + bias) with the small-footprint mma.sync kernel (xvec_linear_small): x bf16 (rows, k), weight bf16 (n, k)
-    row-major (the nn.Linear layout), float32 accumulation; float32 or bf16 result (rows, n)."""
+    """y = act(x W' + bias) with the small-footprint mma.sync kernel (xvec_linear_small): x (rows, k) and weight (n, k)
+    row-major (the nn.Linear layout), both bf16 or both float32 (TF32 math), float32 accumulation; float32 or bf16 result."""
     _require_cuda(x, weight, bias)
     lib = _lib.load()
-    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
-        raise ValueError("linear_small takes bfloat16 operands")
+    if x.dtype != weight.dtype:
+        raise ValueError("x and weight must share a dtype (bfloat16 or float32)")
     x_ld, w_ld = _rowmajor_2d(x, "x"), _rowmajor_2d(weight, "weight")
     if x.shape[1] != weight.shape[1]:
         raise ValueError("x and weight disagree on k")
     out = torch.empty((x.shape[0], weight.shape[0]), dtype=out_dtype, device=x.device)
     b = None if bias is None else bias.detach().float().contiguous()
     with torch.cuda.device(x.device):
-        check(lib.xvec_linear_small(ptr(x), x.shape[0], x.shape[1], x_ld, ptr(weight), weight.shape[0], w_ld, ptr(b), int(bool(relu)),
-                                    ptr(out), dtype_code(out_dtype), out.stride(0), stream_ptr()))
+        check(lib.xvec_linear_small(ptr(x), dtype_code(x.dtype), x.shape[0], x.shape[1], x_ld, ptr(weight), weight.shape[0], w_ld, ptr(b),
+                                    int(bool(relu)), ptr(out), dtype_code(out_dtype), out.stride(0), stream_ptr()))
     return out

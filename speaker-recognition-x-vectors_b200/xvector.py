@@ -260,9 +260,11 @@ class XVectorModel(nn.Module):
             d.w_packed_dev, d.bias_dev = w.data_ptr(), (b.data_ptr() if b is not None else None)
             d.n, d.cin, d.taps, d.dtype = lin.out_features, lin.in_features, 1, code(w.dtype)
             d.tap_offsets[0] = 0
-            if self.act_dtype == torch.bfloat16 and lin.in_features % 8 == 0:
-                # plain bf16 copy of the weight for xvec_linear_small (runs next to the next batch's resident stack kernel)
-                w_plain = ops.cast(lin.weight.detach().float().contiguous(), torch.bfloat16)
+            if lin.in_features % 8 == 0:
+                # plain copy of the weight in the activation dtype for xvec_linear_small (a small-footprint kernel that runs next to
+                # the next batch's resident stack kernel instead of waiting for free SMs)
+                w32 = lin.weight.detach().float().contiguous()
+                w_plain = w32.clone() if self.act_dtype == torch.float32 else ops.cast(w32, self.act_dtype)
                 keep.append(w_plain)
                 d.w_plain_dev = w_plain.data_ptr()
         res = {"tdnn": tdnn, "n_tdnn": len(layers), "fc": fc, "n_fc": len(fcs), "keep": (stack, keep, scale5, shift5, window), "window": window,
