@@ -10,8 +10,8 @@
 // 325 us step.  This kernel fits NEXT TO a resident stack CTA (128 threads, 5 KiB of shared memory, < 64 registers, no TMEM),
 // so the tail of batch i runs concurrently with the stack kernel of batch i+1.  Fixed summation order, no split-K, no atomics.
 //
-// CTA tile 32 x 32, K step of 64 bytes per row (32 bf16 / 16 float32; registers prefetch the next step while the tensor cores
-// work on the current one), 4 warps x (16 x 16) via ldmatrix + mma.sync.m16n8k16.bf16 / m16n8k8.tf32 (ldmatrix on 32-bit data
+// CTA tile 32 x 32, K step of 64 bytes per row (32 bf16 / 16 float32; six steps of operands in flight in registers, the loop
+// is bound by L2 latency), 4 warps x (16 x 16) via ldmatrix + mma.sync.m16n8k16.bf16 / m16n8k8.tf32 (ldmatrix on 32-bit data
 // hands thread (g, t) the element (row g, column t) of each 8 x 4 block, which is the tf32 fragment layout).
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -23,6 +23,7 @@ namespace xvec {
 constexpr int FS_TILE = 32;         // rows and columns of a CTA tile
 constexpr int FS_ROW_BYTES = 64;    // K bytes per row and step
 constexpr int FS_PITCH_BYTES = 80;  // shared-memory row pitch: ldmatrix rows land in distinct 16-byte bank groups
+constexpr int FS_DEPTH = 6;         // K steps of operands in flight per thread (registers)
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
   const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
@@ -61,22 +62,29 @@ fc_small_kernel(const uint8_t* __restrict__ x, long long ldx_bytes, const uint8_
     rw = (w_ok && k_ok) ? __ldg(wp + s * 4) : zero;
   };
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  uint4 rx, rw;
-  fetch(0, rx, rw);
-  for (int s = 0; s < steps; ++s) {
-    *reinterpret_cast<uint4*>(&xs[lrow * FS_PITCH_BYTES + lchunk * 16]) = rx;
-    *reinterpret_cast<uint4*>(&ws[lrow * FS_PITCH_BYTES + lchunk * 16]) = rw;
-    __syncthreads();
-    if (s + 1 < steps) fetch(s + 1, rx, rw);  // in flight while this step is multiplied
+  // FS_DEPTH steps of operands in flight in registers: the loop is bound by the L2 latency of these loads, not by the math
+  uint4 rx[FS_DEPTH], rw[FS_DEPTH];
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {  // two 32-byte K blocks per step
-      uint32_t a[4], b[4];
-      ldmatrix_x4(a, &xs[(16 * wm + (lane & 7) + 8 * ((lane >> 3) & 1)) * FS_PITCH_BYTES + 32 * kk + 16 * (lane >> 4)]);
-      ldmatrix_x4(b, &ws[(16 * wn + (lane & 7) + 8 * (lane >> 4)) * FS_PITCH_BYTES + 32 * kk + 16 * ((lane >> 3) & 1)]);
-      mma_16x8<kTf32>(acc[0], a, b[0], b[1]);
-      mma_16x8<kTf32>(acc[1], a, b[2], b[3]);
+  for (int j = 0; j < FS_DEPTH; ++j) fetch(j, rx[j], rw[j]);
+  for (int s0 = 0; s0 < steps; s0 += FS_DEPTH) {
+#pragma unroll
+    for (int j = 0; j < FS_DEPTH; ++j) {
+      const int s = s0 + j;
+      if (s >= steps) break;
+      *reinterpret_cast<uint4*>(&xs[lrow * FS_PITCH_BYTES + lchunk * 16]) = rx[j];
+      *reinterpret_cast<uint4*>(&ws[lrow * FS_PITCH_BYTES + lchunk * 16]) = rw[j];
+      __syncthreads();
+      fetch(s + FS_DEPTH, rx[j], rw[j]);  // past the end: zero, no access
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {  // two 32-byte K blocks per step
+        uint32_t a[4], b[4];
+        ldmatrix_x4(a, &xs[(16 * wm + (lane & 7) + 8 * ((lane >> 3) & 1)) * FS_PITCH_BYTES + 32 * kk + 16 * (lane >> 4)]);
+        ldmatrix_x4(b, &ws[(16 * wn + (lane & 7) + 8 * (lane >> 4)) * FS_PITCH_BYTES + 32 * kk + 16 * ((lane >> 3) & 1)]);
+        mma_16x8<kTf32>(acc[0], a, b[0], b[1]);
+        mma_16x8<kTf32>(acc[1], a, b[2], b[3]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
