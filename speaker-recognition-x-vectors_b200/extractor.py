@@ -43,7 +43,7 @@ class HostExtractor:
         """Size the staging buffer, the pinned result buffer and the model scratch of every slot for batches of up to
         max_rows frames / max_utts utterances (allocation synchronises the device; do it before the pipeline runs)."""
         dim = (self.model.segment_layer7 if self.model.x_vec_extract_layer == 7 else self.model.segment_layer6).out_features
-        pooled_slots = max_rows // 128 + max_utts + 2  # partial slots: one per 128-frame group + one per utterance boundary
+        pooled_slots = max_rows // 128 + 2 * max_utts + 2  # partial slots: an utterance of n pooled frames touches <= n/128 + 2 groups
         with torch.cuda.device(self.device):
             for i, sl in enumerate(self.slots):
                 if sl.x_dev is None or sl.x_dev.shape[0] < max_rows or sl.x_dev.shape[1] != channels:
