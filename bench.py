@@ -252,7 +252,7 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD,
                        "global_batch": BATCH * world, "frames": FRAMES, "parallelism": f"utterance-sharded x{world}, no data-path collective",
                        "l2": f"inputs larger than L2: {n_res} distinct device-resident batches ({n_res * BATCH * FRAMES * CEPS * 4 >> 20} MiB) cycled; "
-                             "2 batches in flight, activations of the two (4 x 78 MB) also exceed the 126 MB L2",
+                             "2 batches in flight; the stack kernel's banded schedule deliberately keeps one band's activations (2 x 22 MB) L2-resident between layers",
                        "tdnn1": "TF32 math on the float32 MFCCs in both modes (window form: one K = 120 GEMM over overlapping rows)"},
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": hx.h2d_bytes // args.steps, "d2h_bytes_per_step": hx.d2h_bytes // args.steps,
                     "api": "HostExtractor.submit/result (pinned host MFCCs in, pinned host x-vectors out, 6 slots / streams)",
@@ -268,7 +268,9 @@ def run_b200(args, rank, world, local_rank):
                          "frac_of_burst_peak": achieved / (peaks["bf16_tflops"] if precision == "bf16" else peaks["bf16_tflops"] / 2),
                          "algorithmic_flops_per_launch": tdnn_flops, "ms_per_launch": stack_ms,
                          "timing": "CUDA events around each launch on its stream, launches back to back on one stream, averaged"},
-            "per_layer_launches": per_layer,  # the same layers as one tdnn_gemm_kernel launch each (XVEC_STACK=0 path), for comparison
+            # for comparison only: the same layers as one tdnn_gemm_kernel launch each (the XVEC_STACK=0 / XVEC_FC_SMALL=0 path;
+            # segment6 here is the tcgen05 split-K GEMM + reduce, the product runs it on fc_small_kernel)
+            "per_layer_launches": per_layer,
         }
         if world == 1:
             line["roofline_pool"] = pooling_roofline(model, dev, peaks)
