@@ -185,7 +185,7 @@ XVEC_API int xvec_tdnn_stack(const struct XvecLayerDesc* tdnn_host, int n_tdnn, 
 XVEC_API int xvec_linear_small(const void* x_dev, int dtype, int64_t rows, int k, int64_t x_ld, const void* w_dev, int n, int64_t w_ld,
                       const float* bias_dev, int relu, void* y_dev, int y_dtype, int64_t y_ld, void* stream);
 
-/* The whole extraction path for one flat batch in ONE call (4 kernel launches enqueued on `stream`, no host work besides
+/* The whole extraction path for one flat batch in ONE call (3 kernel launches + one 5 KB memset enqueued on `stream`, no host work besides
  * the tensor-map encodes): xvec_tdnn_stack, xvec_pool_finalize, then the n_fc segment layers (ReLU between them, none after
  * the last; xvec_linear_small when the layer carries w_plain_dev, else xvec_tdnn_layer with split-K).  Without ctrl_dev (NULL) or for a stack xvec_tdnn_stack does not take, the TDNN layers run as one launch each
  * (xvec_tdnn_layer / xvec_tdnn_pool_fused) — same results.
