@@ -172,6 +172,14 @@ typedef struct XvecLayerDesc {
  *   ctrl_dev: 128-byte aligned scratch of xvec_stack_ctrl_bytes(rows, n_tdnn) bytes, private to this call until it completes
  *   (the call zeroes it on `stream`).  Returns XVEC_E_ARG for stacks outside these limits (use the per-layer calls). */
 XVEC_API int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn);
+/* Host-side replay of xvec_tdnn_stack's work-item order (needs no GPU; used by the CPU tests): items_out_host[i] =
+ * layer | n_tile << 3 | m_tile << 8 of the i-th item the CTA pairs draw, for n_layers layers with n_tiles_per_layer_host[]
+ * 256-channel tiles over `rows` frame rows; band = m-tiles per scheduling band, 0 = the library's default.  Returns the
+ * number of items (writes at most `capacity` of them; items_out_host may be NULL) or a negative XVEC_E_* code.
+ * The order must list every (layer, m_tile, n_tile) once and every tile after the tiles (layer-1, m_tile-1 .. m_tile+1) it
+ * depends on: with in-order drawing that is what makes the dependency waits deadlock-free. */
+XVEC_API int64_t xvec_stack_plan(int64_t rows, int n_layers, const int32_t* n_tiles_per_layer_host, int band, uint32_t* items_out_host,
+                        int64_t capacity);
 XVEC_API int xvec_tdnn_stack(const struct XvecLayerDesc* tdnn_host, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld,
                     void* act0_dev, void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev,
                     float* part_dev, void* ctrl_dev, int64_t ctrl_bytes, void* stream);

@@ -131,6 +131,10 @@ int xvec_tdnn_pool_fused(const void* x_dev, int x_dtype, int64_t x_rows, int cin
 }
 
 int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn) { return stack_ctrl_bytes(rows, n_tdnn); }
+int64_t xvec_stack_plan(int64_t rows, int n_layers, const int32_t* n_tiles_per_layer_host, int band, uint32_t* items_out_host,
+                        int64_t capacity) {
+  return stack_plan(rows, n_layers, n_tiles_per_layer_host, band, items_out_host, capacity);
+}
 
 int xvec_linear_small(const void* x_dev, int dtype, int64_t rows, int k, int64_t x_ld, const void* w_dev, int n, int64_t w_ld,
                       const float* bias_dev, int relu, void* y_dev, int y_dtype, int64_t y_ld, void* stream) {

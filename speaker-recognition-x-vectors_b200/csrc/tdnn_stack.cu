@@ -90,7 +90,7 @@ __host__ __device__ inline int band_layer_range(int band, int m_tiles, int b, in
   *lo = a;
   return z > a ? z - a : 0;
 }
-__device__ __forceinline__ uint32_t decode_item(const StackParams& p, unsigned item, int& band_cursor) {
+__host__ __device__ inline uint32_t decode_item(const StackParams& p, unsigned item, int& band_cursor) {
   while (item >= p.band_first[band_cursor + 1]) ++band_cursor;
   unsigned r = item - p.band_first[band_cursor];
   for (int l = 0; l < p.n_layers; ++l) {
@@ -535,6 +535,48 @@ static int pick_band(int m_tiles, int n_layers, int pairs) {
   return band;
 }
 
+// Work-item order of a stack whose m_tiles / n_layers / L[].n_tiles are set: band table + total (see decode_item).
+static int fill_schedule(StackParams& p, int band) {
+  p.band = band;
+  p.n_bands = (p.m_tiles + p.n_layers - 1 + p.band - 1) / p.band;
+  if (p.n_bands > XVEC_STACK_MAX_BANDS) return set_error(XVEC_E_ARG, "internal: too many bands");
+  unsigned acc = 0;
+  int64_t items_per_mtile = 0;
+  for (int l = 0; l < p.n_layers; ++l) items_per_mtile += p.L[l].n_tiles;
+  for (int b = 0; b < p.n_bands; ++b) {
+    p.band_first[b] = acc;
+    for (int l = 0; l < p.n_layers; ++l) {
+      int lo;
+      acc += static_cast<unsigned>(band_layer_range(p.band, p.m_tiles, b, l, &lo)) * p.L[l].n_tiles;
+    }
+  }
+  p.band_first[p.n_bands] = acc;
+  if (static_cast<int64_t>(acc) != items_per_mtile * p.m_tiles) return set_error(XVEC_E_ARG, "internal: band table does not cover the stack");
+  p.total_items = acc;
+  return XVEC_OK;
+}
+
+// Host-side replay of the device scheduler's decode (no GPU needed): items_out[i] = (layer | n_tile << 3 | m_tile << 8) of the
+// i-th work item for a stack of n_layers layers with n_tiles_per_layer[] 256-channel tiles over `rows` frame rows.
+int64_t stack_plan(int64_t rows, int n_layers, const int32_t* n_tiles_per_layer, int band, uint32_t* items_out, int64_t capacity) {
+  if (rows <= 0 || n_layers < 2 || n_layers > XVEC_MAX_STACK || !n_tiles_per_layer) return set_error(XVEC_E_ARG, "bad stack shape");
+  static thread_local StackParams p;
+  p = StackParams{};
+  p.m_tiles = static_cast<int>((rows + BM - 1) / BM);
+  p.n_layers = n_layers;
+  for (int l = 0; l < n_layers; ++l) {
+    if (n_tiles_per_layer[l] < 1 || n_tiles_per_layer[l] > 31) return set_error(XVEC_E_ARG, "bad n_tiles");
+    p.L[l].n_tiles = n_tiles_per_layer[l];
+  }
+  int rc = fill_schedule(p, band > 0 ? band : pick_band(p.m_tiles, n_layers, 74));
+  if (rc) return rc;
+  if (items_out) {
+    int cursor = 0;
+    for (unsigned i = 0; i < p.total_items && static_cast<int64_t>(i) < capacity; ++i) items_out[i] = decode_item(p, i, cursor);
+  }
+  return p.total_items;
+}
+
 int64_t stack_ctrl_bytes(int64_t rows, int n_layers) {
   if (rows <= 0 || n_layers < 2) return 0;
   const int64_t m_tiles = (rows + BM - 1) / BM;
@@ -607,7 +649,6 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
   const void* h = x;
   int64_t h_ld = x_ld;
   int h_dtype = tdnn[0].dtype;
-  int64_t items_per_mtile = 0;
   for (int l = 0; l < n_tdnn; ++l) {
     const XvecLayerDesc& d = tdnn[l];
     StackLayer& L = p.L[l];
@@ -625,7 +666,6 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
     L.slab_rows = BM_CTA + max_off;
     L.bias = d.bias_dev;
     if (reinterpret_cast<uintptr_t>(d.bias_dev) & 15u) return set_error(XVEC_E_ARG, "bias must be 16-byte aligned");
-    items_per_mtile += L.n_tiles;
     // window form (h_ld < cin: overlapping rows): only rows whose whole window lies inside the matrix exist, the rest read as zero
     const int64_t h_rows = h_ld < d.cin ? rows - (d.cin + h_ld - 1) / h_ld + 1 : rows;
     if (h_rows <= 0) return set_error(XVEC_E_ARG, "window form: fewer rows than one window");
@@ -655,19 +695,9 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
     local_maps.y[l] = local_maps.a[0];
   }
   const int max_pairs = num_sms() / 2;
-  p.band = pick_band(p.m_tiles, n_tdnn, max_pairs);
-  p.n_bands = (p.m_tiles + n_tdnn - 1 + p.band - 1) / p.band;
-  unsigned acc = 0;
-  for (int b = 0; b < p.n_bands; ++b) {
-    p.band_first[b] = acc;
-    for (int l = 0; l < n_tdnn; ++l) {
-      int lo;
-      acc += static_cast<unsigned>(band_layer_range(p.band, p.m_tiles, b, l, &lo)) * p.L[l].n_tiles;
-    }
-  }
-  p.band_first[p.n_bands] = acc;
-  if (static_cast<int64_t>(acc) != items_per_mtile * p.m_tiles) return set_error(XVEC_E_ARG, "internal: band table does not cover the stack");
-  p.total_items = acc;
+  rc = fill_schedule(p, pick_band(p.m_tiles, n_tdnn, max_pairs));
+  if (rc) return rc;
+  const unsigned acc = p.total_items;
   p.counter = static_cast<unsigned*>(ctrl);
   p.ready = reinterpret_cast<unsigned*>(static_cast<char*>(ctrl) + 128);
   p.row_utt = row_utt;

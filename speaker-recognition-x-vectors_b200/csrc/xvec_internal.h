@@ -27,6 +27,7 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
 // tdnn_stack.cu: all TDNN layers (the last one fused with the pooling partials) as one persistent kernel.
 bool stack_supported(const XvecLayerDesc* tdnn, int n_tdnn, int64_t rows);
 int64_t stack_ctrl_bytes(int64_t rows, int n_layers);
+int64_t stack_plan(int64_t rows, int n_layers, const int32_t* n_tiles_per_layer, int band, uint32_t* items_out, int64_t capacity);
 int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t rows, int64_t x_ld, void* act0, void* act1,
                    int64_t act_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part, void* ctrl, int64_t ctrl_bytes,
                    void* stream);

@@ -161,3 +161,32 @@ def test_load_reference_checkpoint_roundtrip(tmp_path):
     assert not res.missing_keys and not res.unexpected_keys
     for k, v in sd.items():
         assert torch.equal(m.state_dict()[k], v), k
+
+
+@pytest.mark.parametrize("rows,band", [(76800, 0), (76800, 5), (76800, 7), (76800, 1000), (300, 0), (257, 3), (131072, 0), (1536000, 0),
+                                        (40000, 33)])
+def test_stack_schedule_is_a_dependency_respecting_permutation(rows, band):
+    """The work-item order of xvec_tdnn_stack (host replay of the device decode): every (layer, m_tile, n_tile) exactly once, and
+    every tile after ALL tiles (layer-1, m_tile-1..m_tile+1, any n) it waits for — the precondition that makes in-order
+    drawing + dependency flags deadlock-free for any number of resident CTA pairs."""
+    import ctypes
+    lib = xvec_b200._lib.load()
+    n_tiles = [2, 2, 2, 2, 6]  # 512, 512, 512, 512, 1500 channels
+    arr = (ctypes.c_int32 * 5)(*n_tiles)
+    m_tiles = -(-rows // 256)
+    total = lib.xvec_stack_plan(rows, 5, arr, band, None, 0)
+    assert total == m_tiles * sum(n_tiles), lib.xvec_last_error()
+    items = np.empty(total, dtype=np.uint32)
+    assert lib.xvec_stack_plan(rows, 5, arr, band, items.ctypes.data_as(ctypes.c_void_p), total) == total
+    layer, nt, mt = items & 7, (items >> 3) & 31, (items >> 8).astype(np.int64)
+    assert layer.max() == 4 and (nt < np.asarray(n_tiles)[layer]).all() and mt.max() == m_tiles - 1
+    key = (layer.astype(np.int64) * m_tiles + mt) * 8 + nt
+    assert np.unique(key).size == total  # a permutation
+    # position of the LAST item of every (layer, m_tile): a consumer must come after it
+    last = np.full((5, m_tiles), -1, dtype=np.int64)
+    np.maximum.at(last, (layer, mt), np.arange(total))
+    pos = np.arange(total)
+    for d in (-1, 0, 1):
+        m_dep = mt + d
+        ok = (layer > 0) & (m_dep >= 0) & (m_dep < m_tiles)
+        assert (last[layer[ok] - 1, m_dep[ok]] < pos[ok]).all()
