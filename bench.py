@@ -252,7 +252,7 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD,
                        "global_batch": BATCH * world, "frames": FRAMES, "parallelism": f"utterance-sharded x{world}, no data-path collective",
                        "l2": f"inputs larger than L2: {n_res} distinct device-resident batches ({n_res * BATCH * FRAMES * CEPS * 4 >> 20} MiB) cycled; "
-                             "2 batches in flight; the stack kernel's banded schedule deliberately keeps one band's activations (2 x 22 MB) L2-resident between layers",
+                             "2 batches in flight; the stack kernel's banded schedule deliberately keeps one band's activations (2 x 43.5 MB in bf16) L2-resident between layers",
                        "tdnn1": "TF32 math on the float32 MFCCs in both modes (window form: one K = 120 GEMM over overlapping rows)"},
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": hx.h2d_bytes // args.steps, "d2h_bytes_per_step": hx.d2h_bytes // args.steps,
                     "api": "HostExtractor.submit/result (pinned host MFCCs in, pinned host x-vectors out, 6 slots / streams)",

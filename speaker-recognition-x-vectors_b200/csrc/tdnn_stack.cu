@@ -521,7 +521,8 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
 // Band height.  Two opposing effects, both measured on B200 (256 x 300 frames = 300 m-tiles, bf16, 74 pairs):
 //   * producers run 3-4 tiles ahead of the published completions, so an item's inputs are only certain to be complete when they
 //     were drawn >= ~4 x pairs items earlier — bands of 100 / 148 m-tiles stall (364 us sustained, dependency warps spinning);
-//   * a band's activations (band x 128 KiB per layer and buffer) stay in L2 between the layers when the band is short enough,
+//   * a band's activations (band x 256 KiB per ping-pong buffer in bf16: 2 x 43.5 MB at 170 m-tiles, of 126 MB of L2) stay in
+//     L2 between the layers when the band is short enough,
 //     which saves the HBM round trip of every activation and the power that goes with it — the kernel runs at the 1000 W cap,
 //     so this is throughput: one band 294 / 336 us (burst / sustained), bands of 160-170: 278 / 322 us, 180-200: 282-284 /
 //     326-328 us, 225: 292 / 332 us, 250: 311 / 347 us.  64 x 6000 frames (1500 m-tiles): 1474 -> 1382 us; 437 x 300: 519 -> 467 us.
