@@ -526,11 +526,18 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
 //     which saves the HBM round trip of every activation and the power that goes with it — the kernel runs at the 1000 W cap,
 //     so this is throughput: one band 294 / 336 us (burst / sustained), bands of 160-170: 278 / 322 us, 180-200: 282-284 /
 //     326-328 us, 225: 292 / 332 us, 250: 311 / 347 us.  64 x 6000 frames (1500 m-tiles): 1474 -> 1382 us; 437 x 300: 519 -> 467 us.
-// Hence bands of 2.3 x pairs m-tiles.  XVEC_BAND overrides (developer A/B switch).
+// Hence equal bands of about 2.3 x pairs m-tiles.  XVEC_BAND overrides (developer A/B switch).
 static int pick_band(int m_tiles, int n_layers, int pairs) {
   const char* e = getenv("XVEC_BAND");
   const int env = e ? atoi(e) : 0;
-  int band = env > 0 ? env : (23 * pairs + 5) / 10;
+  int band = env;
+  if (band <= 0) {
+    // equal bands of about 2.3 x pairs m-tiles: a short last band runs its five layers as a serial chain of a few tiles each
+    // (437 x 300 frames = 512 m-tiles: bands 170+170+170+6 take 525 us, 3 x 172 take 487 us)
+    const int target = (23 * pairs + 5) / 10, span = m_tiles + n_layers - 1;
+    const int n_bands = span < target ? 1 : (span + target / 2) / target;
+    band = (span + n_bands - 1) / n_bands;
+  }
   if (band < n_layers) band = n_layers;
   while ((m_tiles + n_layers - 1 + band - 1) / band > XVEC_STACK_MAX_BANDS) band *= 2;
   return band;
