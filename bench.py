@@ -140,23 +140,38 @@ def cpu_baseline_leg(budget_s=12.0):
             "frames_per_sec": 64 * FRAMES / med, "gflops": 64 * flops_per_utt(FRAMES) / med / 1e9, "best_utt_s": 64 / times[0]}
 
 
+def synthetic_model(xvec_b200, precision):
+    """Random-init weights of the reference architecture (PyTorch default initialisers, as main.XVectorModel() gets them) with
+    non-trivial eval-mode BatchNorm statistics (default-init BN is the identity and would make the BN fold free)."""
+    import torch
+    torch.manual_seed(0)
+    model = xvec_b200.XVectorModel(precision=precision)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for layer in model.time_context_layers:
+            n = layer.norm.num_features
+            layer.norm.running_mean.copy_(0.5 * torch.randn(n, generator=g))
+            layer.norm.running_var.copy_(0.3 + 1.7 * torch.rand(n, generator=g))
+            layer.norm.weight.copy_(1.0 + 0.5 * torch.randn(n, generator=g))
+            layer.norm.bias.copy_(0.5 * torch.randn(n, generator=g))
+    return model
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    import xvec_b200
-    from oracle import xvector_oracle as ox  # only for seeded synthetic weights/inputs and the cpu_baseline leg
+    import xvec_b200  # the product; nothing under oracle/ is imported on this arm except by cpu_baseline_leg()
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     precision = args.dtype
-    model = xvec_b200.XVectorModel(precision=precision)
-    model.load_state_dict(ox.make_state_dict(seed=0))
-    model = model.to(dev).eval()
+    model = synthetic_model(xvec_b200, precision).to(dev).eval()
 
     n_batches = N_UTTS // BATCH
-    x_host = ox.synth_mfcc(N_UTTS, FRAMES, seed=1234 + rank).reshape(n_batches, BATCH * FRAMES, CEPS).pin_memory()
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(N_UTTS, FRAMES, CEPS, generator=g).reshape(n_batches, BATCH * FRAMES, CEPS).pin_memory()
     # device-resident inputs: the 1024-utterance set replicated (with a per-copy scale) to N_RESIDENT distinct batches so that
     # the inputs cycled through the timed region (N_RESIDENT x 7.4 MB) are larger than the 126 MB L2
     n_res = max(n_batches, -(-(160 << 20) // (BATCH * FRAMES * CEPS * 4)))
