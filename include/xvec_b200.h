@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XVEC_ABI_VERSION 4
+#define XVEC_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define XVEC_API __attribute__((visibility("default")))
@@ -49,13 +49,17 @@ extern "C" {
 #define XVEC_POOL_CHUNK 128 /* rows per partial of the standalone statistics-pooling kernel */
 #define XVEC_MAX_STACK 6           /* TDNN layers xvec_tdnn_stack can chain in one launch */
 #define XVEC_STACK_MAX_BANDS 512   /* scheduling bands of xvec_tdnn_stack (internal table size) */
+#define XVEC_STACK_MAX_TAP_OFFSET 8 /* largest c_j - c_0 xvec_tdnn_stack takes (one activation slab holds 128 + 8 frame rows) */
 
 XVEC_API int xvec_abi_version(void);
 XVEC_API const char* xvec_last_error(void);
 /* 0 if the current CUDA device can run these kernels (compute capability 10.x), else XVEC_E_DEVICE. */
 XVEC_API int xvec_device_check(void);
-/* Value left by the device-side pipeline watchdog (0 = never fired). Synchronises the device. */
+/* Value left by the device-side pipeline watchdog (0 = never fired): every mbarrier wait / flag spin of the tcgen05 kernels
+ * traps after a bounded number of polls and first writes which wait it was (1-8) into a word of mapped HOST memory, so the code
+ * survives the failed launch (a trap destroys the context).  Synchronises the device.  xvec_watchdog_reset() clears it. */
 XVEC_API int xvec_watchdog_code(void);
+XVEC_API void xvec_watchdog_reset(void);
 
 /* Developer aid: with XVEC_TRACE=1 in the environment the GEMM kernel records per-tile clock64 stamps of CTA 0;
  * copies up to n of them to out_host and returns the count (0 when tracing is off). */
@@ -125,21 +129,25 @@ XVEC_API int xvec_build_layout(const int32_t* starts_dev, const int32_t* n_pool_
  *   x_dev (.., p) of x_dtype with row stride x_ld elements; p multiple of 4
  *   row_start_dev int64 (n_utts), n_rows_dev int32 (n_utts), slot_start_dev int32 (n_utts+1) = exclusive prefix
  *   sum of ceil(n_rows/XVEC_POOL_CHUNK); max_chunks = max over utterances of that count.
+ *   pivot_dev float32 (n_utts, p), 16-byte aligned, or NULL: when given, the sums are taken of x - pivot with pivot = the
+ *   utterance's first row (written here, passed on to xvec_pool_finalize) — a one-pass float32 sum of squares otherwise loses
+ *   the variance of inputs with |mean| >> std, which the reference's two-pass torch.std (main.py:61) does not.
  */
 XVEC_API int xvec_stats_pool_partial(const void* x_dev, int x_dtype, int64_t x_ld, int p, const int64_t* row_start_dev,
                             const int32_t* n_rows_dev, const int32_t* slot_start_dev, int n_utts, int max_chunks,
-                            float* part_dev, void* stream);
+                            float* part_dev, float* pivot_dev, void* stream);
 
 /* Statistics pooling, second half: deterministic fixed-order (float64) reduction of an utterance's partial slots
  * [slot_start[u], slot_start[u+1]) and the final statistics
  *   mean = s*(S/n) + h,   std = |s| * sqrt( (Q - S*S/n) / (n-1) )       (unbiased, torch.std default; n==1 -> NaN)
  * replaces: torch.mean, torch.std, torch.cat in stat_pool (main.py:60-62) (+ the BatchNorm of TDNN5 folded
  * through the statistics when bn_scale/shift are given; both NULL = plain pooling).
+ *   pivot_dev float32 (n_utts, p) or NULL: the partial sums are of x - pivot (xvec_stats_pool_partial); the mean gets it back.
  *   out_f32_dev float32 (n_utts, 2p) [mean || std], row stride 2p;  out_lp_dev optional second copy in out_lp_dtype
  *   with row stride out_lp_ld (feeds segment_layer6 directly), or NULL.
  */
 XVEC_API int xvec_pool_finalize(const float* part_dev, const int32_t* slot_start_dev, const int32_t* n_rows_dev, int n_utts,
-                       int p, const float* bn_scale_dev, const float* bn_shift_dev, float* out_f32_dev,
+                       int p, const float* bn_scale_dev, const float* bn_shift_dev, const float* pivot_dev, float* out_f32_dev,
                        void* out_lp_dev, int out_lp_dtype, int64_t out_lp_ld, void* stream);
 
 /* One layer of xvec_extract_forward: a TDNN layer (taps >= 1) or a fully connected layer (taps == 1), operands already
@@ -170,7 +178,9 @@ typedef struct XvecLayerDesc {
  *   are don't-care rows of the last utterance anyway) read as zero; nothing past the end of x_dev is touched.
  *   xvec_tdnn_layer / xvec_tdnn_pool_fused accept the same form.
  *   ctrl_dev: 128-byte aligned scratch of xvec_stack_ctrl_bytes(rows, n_tdnn) bytes, private to this call until it completes
- *   (the call zeroes it on `stream`).  Returns XVEC_E_ARG for stacks outside these limits (use the per-layer calls). */
+ *   (the call zeroes it on `stream`).  band: m-tiles per scheduling band, 0 = the library's choice (any value gives the same
+ *   bits; tests sweep it).  Tap offsets up to XVEC_STACK_MAX_TAP_OFFSET.  Returns XVEC_E_ARG for stacks outside these limits
+ *   (use the per-layer calls).  The encoded tensor maps of the last 64 distinct argument sets are cached inside the library. */
 XVEC_API int64_t xvec_stack_ctrl_bytes(int64_t rows, int n_tdnn);
 /* Host-side replay of xvec_tdnn_stack's work-item order (needs no GPU; used by the CPU tests): items_out_host[i] =
  * layer | n_tile << 3 | m_tile << 8 of the i-th item the CTA pairs draw, for n_layers layers with n_tiles_per_layer_host[]
@@ -182,7 +192,7 @@ XVEC_API int64_t xvec_stack_plan(int64_t rows, int n_layers, const int32_t* n_ti
                         int64_t capacity);
 XVEC_API int xvec_tdnn_stack(const struct XvecLayerDesc* tdnn_host, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld,
                     void* act0_dev, void* act1_dev, int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev,
-                    float* part_dev, void* ctrl_dev, int64_t ctrl_bytes, void* stream);
+                    float* part_dev, void* ctrl_dev, int64_t ctrl_bytes, int band, void* stream);
 
 /* Small-footprint linear layer: y = act(x W' + bias), x (rows, k) and W (n, k) row-major (the nn.Linear layout, NOT packed) of
  * `dtype` (XVEC_BF16, or XVEC_F32 = TF32 math), float32 accumulation, y float32 or bfloat16.  128 threads, 5 KiB of shared

@@ -16,8 +16,9 @@ LIB_PATH = os.environ.get("XVEC_LIB") or os.path.join(HERE, "libxvec_b200.so")  
 F32, BF16 = 0, 1
 E_ARG, E_CUDA, E_DEVICE = -1, -2, -3
 TILE_N, POOL_BLOCK, POOL_CHUNK, MAX_TAPS = 256, 128, 128, 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_STACK = 6
+STACK_MAX_TAP_OFFSET = 8  # XVEC_STACK_MAX_TAP_OFFSET
 
 class LayerDesc(ctypes.Structure):
     """XvecLayerDesc of include/xvec_b200.h."""
@@ -30,6 +31,7 @@ _SIGNATURES = {
     "xvec_last_error": (c_char_p, []),
     "xvec_device_check": (c_int, []),
     "xvec_watchdog_code": (c_int, []),
+    "xvec_watchdog_reset": (None, []),
     "xvec_debug_trace": (c_int, [c_void_p, c_int]),
     "xvec_packed_k": (c_int64, [c_int, c_int, c_int]),
     "xvec_packed_n": (c_int64, [c_int]),
@@ -41,8 +43,8 @@ _SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "xvec_build_layout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "xvec_stats_pool_partial": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                        c_void_p, c_void_p]),
-    "xvec_pool_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "xvec_pool_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int64, c_void_p]),
     "xvec_extract_forward": (c_int, [POINTER(LayerDesc), c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LayerDesc), c_int,
@@ -52,7 +54,7 @@ _SIGNATURES = {
     "xvec_linear_small": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_int64,
                                   c_void_p]),
     "xvec_tdnn_stack": (c_int, [POINTER(LayerDesc), c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_int64, c_void_p]),
+                                c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "xvec_mfcc_num_frames": (c_int64, [c_int64]),
     "xvec_mfcc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "xvec_wav_minmax": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -24,10 +24,13 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+DEBUG_LIB = os.path.join(HERE, "libxvec_b200_debug.so")
+
+
+def needs_build(lib: str = LIB) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -41,7 +44,9 @@ def build(force: bool = False, verbose: bool = False, debug: bool = False) -> st
     """debug=True builds libxvec_b200_debug.so with -DXVEC_DEBUG (per-tile clock stamps and epilogue/mainloop skip switches
     for tools/trace_tiles.py etc.; select it with XVEC_LIB=...)."""
     if debug:
-        return _build_to(os.path.join(HERE, "libxvec_b200_debug.so"), list(NVCC_FLAGS) + ["-DXVEC_DEBUG"], verbose, "_dbg")
+        if not force and not needs_build(DEBUG_LIB):
+            return DEBUG_LIB
+        return _build_to(DEBUG_LIB, list(NVCC_FLAGS) + ["-DXVEC_DEBUG"], verbose, "_dbg")
     if not force and not needs_build():
         return LIB
     return _build_to(LIB, list(NVCC_FLAGS), verbose, "")

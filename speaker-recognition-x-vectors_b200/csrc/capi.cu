@@ -55,36 +55,55 @@ int num_sms() {
 }
 
 PFN_encodeTiled get_encode_tiled() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
+  static const PFN_encodeTiled fn = [] {  // initialised once, thread-safe (C++11 local static)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
+      return reinterpret_cast<PFN_encodeTiled>(p);
+    return static_cast<PFN_encodeTiled>(nullptr);
+  }();
   return fn;
 }
 
-// XVEC_STACK=0 makes xvec_extract_forward run one launch per layer (developer A/B switch; both are sm_100a paths).
-static bool use_stack_kernel() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("XVEC_STACK");
-    v = (e && e[0] == '0') ? 0 : 1;
+unsigned int* watchdog_host_word() {
+  static std::mutex mu;
+  static unsigned int* word = nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!word) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    word = static_cast<unsigned int*>(p);
+    *word = 0u;
   }
-  return v == 1;
+  return word;
 }
 
-// XVEC_FC_SMALL=0 keeps the segment layers on the tcgen05 kernel (developer A/B switch).
-static bool use_fc_small() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("XVEC_FC_SMALL");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
+int read_watchdog() {
+  unsigned int* w = watchdog_host_word();
+  return w ? static_cast<int>(*reinterpret_cast<volatile unsigned int*>(w)) : 0;
 }
+
+// Developer A/B switches exist in -DXVEC_DEBUG builds only (libxvec_b200_debug.so); the product library reads no environment.
+//   XVEC_STACK=0     xvec_extract_forward runs one launch per TDNN layer
+//   XVEC_FC_SMALL=0  the segment layers stay on the tcgen05 kernel
+#ifdef XVEC_DEBUG
+static bool env_switch_on(const char* name) {
+  const char* e = getenv(name);
+  return !(e && e[0] == '0');
+}
+static bool use_stack_kernel() {
+  static const bool v = env_switch_on("XVEC_STACK");
+  return v;
+}
+static bool use_fc_small() {
+  static const bool v = env_switch_on("XVEC_FC_SMALL");
+  return v;
+}
+#else
+static constexpr bool use_stack_kernel() { return true; }
+static constexpr bool use_fc_small() { return true; }
+#endif
 
 }  // namespace xvec
 
@@ -96,8 +115,11 @@ int xvec_abi_version(void) { return XVEC_ABI_VERSION; }
 const char* xvec_last_error(void) { return g_err; }
 int xvec_device_check(void) { return device_check(); }
 int xvec_watchdog_code(void) {
-  cudaDeviceSynchronize();
+  cudaDeviceSynchronize();  // after a trap this reports the sticky launch failure; the word lives in host memory
   return read_watchdog();
+}
+void xvec_watchdog_reset(void) {
+  if (unsigned int* w = watchdog_host_word()) *reinterpret_cast<volatile unsigned int*>(w) = 0u;
 }
 
 int xvec_debug_trace(long long* out_host, int n) { return read_trace(out_host, n); }
@@ -143,10 +165,10 @@ int xvec_linear_small(const void* x_dev, int dtype, int64_t rows, int k, int64_t
 
 int xvec_tdnn_stack(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld, void* act0_dev, void* act1_dev,
                     int64_t act_ld, const int32_t* row_utt_dev, const int32_t* blk_slot_base_dev, float* part_dev, void* ctrl_dev,
-                    int64_t ctrl_bytes, void* stream) {
+                    int64_t ctrl_bytes, int band, void* stream) {
   if (!tdnn) return set_error(XVEC_E_ARG, "tdnn_host is NULL");
   return stack_dispatch(tdnn, n_tdnn, x_dev, rows, x_ld, act0_dev, act1_dev, act_ld, row_utt_dev, blk_slot_base_dev, part_dev, ctrl_dev,
-                        ctrl_bytes, stream);
+                        ctrl_bytes, band, stream);
 }
 
 int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_dev, int64_t rows, int64_t x_ld, void* act0_dev,
@@ -162,7 +184,7 @@ int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_de
   int rc;
   if (ctrl_dev && use_stack_kernel() && stack_supported(tdnn, n_tdnn, rows)) {
     rc = stack_dispatch(tdnn, n_tdnn, x_dev, rows, x_ld, act0_dev, act1_dev, act_ld, row_utt_dev, blk_slot_base_dev, part_dev, ctrl_dev,
-                        ctrl_bytes, stream);
+                        ctrl_bytes, 0, stream);
     if (rc) return rc;
   } else {
     void* act[2] = {act0_dev, act1_dev};
@@ -187,7 +209,7 @@ int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_de
 #endif
   const int fc_in_dtype = fc[0].dtype;
   if (fc_in_dtype == XVEC_BF16 && !pooled_lp_dev) return set_error(XVEC_E_ARG, "pooled_lp_dev is required for bf16 segment layers");
-  rc = xvec_pool_finalize(part_dev, utt_slot_start_dev, n_pool_dev, n_utts, last.n, bn_last_scale_dev, bn_last_shift_dev, pooled_dev,
+  rc = xvec_pool_finalize(part_dev, utt_slot_start_dev, n_pool_dev, n_utts, last.n, bn_last_scale_dev, bn_last_shift_dev, nullptr, pooled_dev,
                           fc_in_dtype == XVEC_BF16 ? pooled_lp_dev : nullptr, XVEC_BF16, 2 * static_cast<int64_t>(last.n), stream);
   if (rc) return rc;
 #ifdef XVEC_DEBUG

@@ -124,10 +124,11 @@ __device__ __forceinline__ void pool_epilogue_tile_t(const PoolArgs& p, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// L2 promotion of the TMA loads (XVEC_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B; developer A/B switch).  Measured on the stack
-// kernel: none / 64 B / 128 B 302.8 us, 256 B 305.5 us — every box row is one 128-byte line, 256 B promotion fetches a neighbour
-// line another CTA may not want yet.
+// L2 promotion of the TMA loads.  Measured on the stack kernel: none / 64 B / 128 B 302.8 us, 256 B 305.5 us — every box row is
+// one 128-byte line, 256 B promotion fetches a neighbour line another CTA may not want yet.  Debug builds: XVEC_L2PROMO = 0
+// none, 1 64 B, 2 128 B, 3 256 B (developer A/B switch; the product library reads no environment).
 inline CUtensorMapL2promotion l2_promotion() {
+#ifdef XVEC_DEBUG
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("XVEC_L2PROMO");
@@ -135,6 +136,9 @@ inline CUtensorMapL2promotion l2_promotion() {
   }
   return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
        : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+#else
+  return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+#endif
 }
 // 2-D row-major tensor map; the inner box is one swizzle-width chunk (128 bytes unless stated).
 inline int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t inner, uint64_t outer, uint64_t ld_elems,
@@ -155,9 +159,10 @@ inline int make_tmap_2d(CUtensorMap* map, const void* ptr, int dtype, uint64_t i
   return XVEC_OK;
 }
 
-// L2 eviction hints of the TMA traffic: activations in, weights, activations out.  XVEC_L2HINT = three digits
-// (0 normal, 1 evict-first, 2 evict-last) overrides the default.
+// L2 eviction hints of the TMA traffic: activations in (evict-first), weights (evict-last), activations out (evict-last).
+// Debug builds: XVEC_L2HINT = three digits (0 normal, 1 evict-first, 2 evict-last) overrides the default.
 inline void l2_policies(unsigned long long* pol_a, unsigned long long* pol_b, unsigned long long* pol_y) {
+#ifdef XVEC_DEBUG
   static const unsigned long long pol_tab[3] = {L2_EVICT_NORMAL, L2_EVICT_FIRST, L2_EVICT_LAST};
   static int hint[3] = {-1, 0, 0};
   if (hint[0] < 0) {
@@ -173,6 +178,11 @@ inline void l2_policies(unsigned long long* pol_a, unsigned long long* pol_b, un
   *pol_a = pol_tab[hint[0]];
   *pol_b = pol_tab[hint[1]];
   *pol_y = pol_tab[hint[2]];
+#else
+  *pol_a = L2_EVICT_FIRST;
+  *pol_b = L2_EVICT_LAST;
+  *pol_y = L2_EVICT_LAST;
+#endif
 }
 
 }  // namespace xvec

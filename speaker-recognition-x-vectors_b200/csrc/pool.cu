@@ -10,10 +10,14 @@ namespace xvec {
 // ------------------------------------------------------------------------------------------------ stats pooling
 // grid = (n_utts, max_chunks, ceil(p / 512)), block = 128: thread owns 4 adjacent columns, the CTA streams
 // XVEC_POOL_CHUNK rows of one utterance; every row read is one contiguous <= 2 KiB segment per CTA.
+// The sums are taken of x - pivot, pivot = the utterance's FIRST row (per column; written to pivot_out by chunk 0): a one-pass
+// sum of squares in float32 loses the variance when |mean| >> std (mean 100, std 1: 1e4 * 2^-24 per term), the shifted sums
+// do not, and mean / variance are shift-invariant — torch.std (main.py:61) is two-pass and has no such limit either.
 template <bool kBf16>
 __global__ void __launch_bounds__(128)
 stats_pool_partial_kernel(const void* __restrict__ x, long long ld, int p, const long long* __restrict__ row_start,
-                          const int* __restrict__ n_rows, const int* __restrict__ slot_start, float* __restrict__ part) {
+                          const int* __restrict__ n_rows, const int* __restrict__ slot_start, float* __restrict__ part,
+                          float* __restrict__ pivot_out) {
   const int u = blockIdx.x;
   const int nr = n_rows[u];
   const int r0 = blockIdx.y * XVEC_POOL_CHUNK;
@@ -23,11 +27,23 @@ stats_pool_partial_kernel(const void* __restrict__ x, long long ld, int p, const
   if (c >= p) return;
   const long long first = row_start[u] + r0;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);  // pivot: the utterance's first row (same for all of its chunks)
+  auto acc = [&](float a, float b, float cc, float d) {
+    a -= pv.x; b -= pv.y; cc -= pv.z; d -= pv.w;
+    s0 += a; s1 += b; s2 += cc; s3 += d;
+    q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1); q2 = fmaf(cc, cc, q2); q3 = fmaf(d, d, q3);
+  };
   constexpr int U = 8;  // independent row loads in flight per thread
   int r = r0;
   if constexpr (kBf16) {
     const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + first * ld + c);
     const long long step = ld / 4;  // uint2 = 4 bf16
+    if (pivot_out) {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + row_start[u] * ld + c));
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+      pv = make_float4(a.x, a.y, b.x, b.y);
+    }
     for (; r + U <= r1; r += U) {
       uint2 v[U];
 #pragma unroll
@@ -36,37 +52,32 @@ stats_pool_partial_kernel(const void* __restrict__ x, long long ld, int p, const
       for (int i = 0; i < U; ++i) {
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[i].x));
         const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[i].y));
-        s0 += a.x; s1 += a.y; s2 += b.x; s3 += b.y;
-        q0 = fmaf(a.x, a.x, q0); q1 = fmaf(a.y, a.y, q1); q2 = fmaf(b.x, b.x, q2); q3 = fmaf(b.y, b.y, q3);
+        acc(a.x, a.y, b.x, b.y);
       }
     }
     for (; r < r1; ++r) {
       const uint2 w = __ldcs(src + static_cast<long long>(r - r0) * step);
       const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
       const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
-      s0 += a.x; s1 += a.y; s2 += b.x; s3 += b.y;
-      q0 = fmaf(a.x, a.x, q0); q1 = fmaf(a.y, a.y, q1); q2 = fmaf(b.x, b.x, q2); q3 = fmaf(b.y, b.y, q3);
+      acc(a.x, a.y, b.x, b.y);
     }
   } else {
     const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + first * ld + c);
     const long long step = ld / 4;
+    if (pivot_out) pv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + row_start[u] * ld + c));
     for (; r + U <= r1; r += U) {
       float4 v[U];
 #pragma unroll
       for (int i = 0; i < U; ++i) v[i] = __ldcs(src + static_cast<long long>(r - r0 + i) * step);
 #pragma unroll
-      for (int i = 0; i < U; ++i) {
-        s0 += v[i].x; s1 += v[i].y; s2 += v[i].z; s3 += v[i].w;
-        q0 = fmaf(v[i].x, v[i].x, q0); q1 = fmaf(v[i].y, v[i].y, q1);
-        q2 = fmaf(v[i].z, v[i].z, q2); q3 = fmaf(v[i].w, v[i].w, q3);
-      }
+      for (int i = 0; i < U; ++i) acc(v[i].x, v[i].y, v[i].z, v[i].w);
     }
     for (; r < r1; ++r) {
       const float4 w = __ldcs(src + static_cast<long long>(r - r0) * step);
-      s0 += w.x; s1 += w.y; s2 += w.z; s3 += w.w;
-      q0 = fmaf(w.x, w.x, q0); q1 = fmaf(w.y, w.y, q1); q2 = fmaf(w.z, w.z, q2); q3 = fmaf(w.w, w.w, q3);
+      acc(w.x, w.y, w.z, w.w);
     }
   }
+  if (pivot_out && blockIdx.y == 0) *reinterpret_cast<float4*>(pivot_out + static_cast<size_t>(u) * p + c) = pv;
   float* dst = part + static_cast<size_t>(slot_start[u] + blockIdx.y) * 2 * p + c;
   *reinterpret_cast<float4*>(dst) = make_float4(s0, s1, s2, s3);
   *reinterpret_cast<float4*>(dst + p) = make_float4(q0, q1, q2, q3);
@@ -75,8 +86,8 @@ stats_pool_partial_kernel(const void* __restrict__ x, long long ld, int p, const
 // grid = (n_utts, ceil(p/128)), block = 128: fixed-order float64 reduction of an utterance's partial slots.
 __global__ void __launch_bounds__(128)
 pool_finalize_kernel(const float* __restrict__ part, const int* __restrict__ slot_start, const int* __restrict__ n_rows, int p,
-                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out,
-                     void* __restrict__ out_lp, int lp_dtype, long long lp_ld) {
+                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ pivot,
+                     float* __restrict__ out, void* __restrict__ out_lp, int lp_dtype, long long lp_ld) {
   const int u = blockIdx.x;
   const int col = blockIdx.y * 128 + threadIdx.x;
   __shared__ double inv_n[2];
@@ -112,7 +123,8 @@ pool_finalize_kernel(const float* __restrict__ part, const int* __restrict__ slo
   // 1/n and 1/(n-1) once per block (float64 division is a long software sequence; per thread it dominated this kernel)
   const int n = n_rows[u];
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  const double mean = n > 0 ? S * inv_n[0] : nan;
+  // the partial sums are of x - pivot (standalone pooling; the fused epilogue passes no pivot): the variance is unchanged
+  const double mean = n > 0 ? S * inv_n[0] + (pivot ? static_cast<double>(pivot[static_cast<size_t>(u) * p + col]) : 0.0) : nan;
   double var = n > 1 ? (Q - S * S * inv_n[0]) * inv_n[1] : nan;  // torch.std: unbiased; a single frame gives NaN
   if (var < 0.0) var = 0.0;
   const float sc = scale ? scale[col] : 1.f;
@@ -312,30 +324,31 @@ int xvec_build_layout(const int32_t* starts_dev, const int32_t* n_pool_dev, cons
 
 int xvec_stats_pool_partial(const void* x_dev, int x_dtype, int64_t x_ld, int p, const int64_t* row_start_dev,
                             const int32_t* n_rows_dev, const int32_t* slot_start_dev, int n_utts, int max_chunks, float* part_dev,
-                            void* stream) {
+                            float* pivot_dev, void* stream) {
   int rc = device_check();
   if (rc) return rc;
   if (!x_dev || !row_start_dev || !n_rows_dev || !slot_start_dev || !part_dev) return set_error(XVEC_E_ARG, "null pointer argument");
   if (x_dtype != XVEC_F32 && x_dtype != XVEC_BF16) return set_error(XVEC_E_ARG, "bad x_dtype %d", x_dtype);
   if (p <= 0 || p % 4 != 0 || x_ld % 4 != 0 || x_ld < p) return set_error(XVEC_E_ARG, "p and x_ld must be positive multiples of 4, x_ld >= p");
   const int align = x_dtype == XVEC_BF16 ? 8 : 16;
-  if ((reinterpret_cast<uintptr_t>(x_dev) % align) != 0 || (reinterpret_cast<uintptr_t>(part_dev) & 15u) != 0)
-    return set_error(XVEC_E_ARG, "x_dev / part_dev are not sufficiently aligned");
+  if ((reinterpret_cast<uintptr_t>(x_dev) % align) != 0 || (reinterpret_cast<uintptr_t>(part_dev) & 15u) != 0 ||
+      (reinterpret_cast<uintptr_t>(pivot_dev) & 15u) != 0)
+    return set_error(XVEC_E_ARG, "x_dev / part_dev / pivot_dev are not sufficiently aligned");
   if (n_utts <= 0 || max_chunks <= 0 || max_chunks > 65535) return set_error(XVEC_E_ARG, "bad n_utts / max_chunks");
   dim3 grid(n_utts, max_chunks, (p + 511) / 512);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_dtype == XVEC_BF16)
     stats_pool_partial_kernel<true><<<grid, 128, 0, st>>>(x_dev, x_ld, p, reinterpret_cast<const long long*>(row_start_dev), n_rows_dev,
-                                                         slot_start_dev, part_dev);
+                                                         slot_start_dev, part_dev, pivot_dev);
   else
     stats_pool_partial_kernel<false><<<grid, 128, 0, st>>>(x_dev, x_ld, p, reinterpret_cast<const long long*>(row_start_dev), n_rows_dev,
-                                                          slot_start_dev, part_dev);
+                                                          slot_start_dev, part_dev, pivot_dev);
   return check_launch("stats_pool_partial_kernel");
 }
 
 int xvec_pool_finalize(const float* part_dev, const int32_t* slot_start_dev, const int32_t* n_rows_dev, int n_utts, int p,
-                       const float* bn_scale_dev, const float* bn_shift_dev, float* out_f32_dev, void* out_lp_dev, int out_lp_dtype,
-                       int64_t out_lp_ld, void* stream) {
+                       const float* bn_scale_dev, const float* bn_shift_dev, const float* pivot_dev, float* out_f32_dev, void* out_lp_dev,
+                       int out_lp_dtype, int64_t out_lp_ld, void* stream) {
   int rc = device_check();
   if (rc) return rc;
   if (!part_dev || !slot_start_dev || !n_rows_dev || !out_f32_dev) return set_error(XVEC_E_ARG, "null pointer argument");
@@ -345,7 +358,8 @@ int xvec_pool_finalize(const float* part_dev, const int32_t* slot_start_dev, con
   if (out_lp_dev && out_lp_ld < 2 * p) return set_error(XVEC_E_ARG, "out_lp_ld < 2p");
   dim3 grid(n_utts, (p + 127) / 128);
   pool_finalize_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(part_dev, slot_start_dev, n_rows_dev, p, bn_scale_dev,
-                                                                            bn_shift_dev, out_f32_dev, out_lp_dev, out_lp_dtype, out_lp_ld);
+                                                                            bn_shift_dev, pivot_dev, out_f32_dev, out_lp_dev, out_lp_dtype,
+                                                                            out_lp_ld);
   return check_launch("pool_finalize_kernel");
 }
 

@@ -8,9 +8,24 @@
 
 namespace xvec {
 
-// Written by a device-side watchdog when an mbarrier wait does not complete; the kernel then traps, so a
-// protocol bug shows up as a launch failure instead of hanging the GPU.
-static __device__ unsigned int g_watchdog_code = 0;
+// Device-side watchdog: when an mbarrier wait or a flag spin does not complete the kernel writes a code and traps, so a
+// protocol bug shows up as a launch failure instead of hanging the GPU.  A trap destroys the context (and every device
+// allocation with it), so the code goes to ONE word of mapped, pinned HOST memory shared by all translation units
+// (capi.cu: watchdog_host_word()); each TU keeps the word's address in its own copy of this pointer, bound once per
+// device by XVEC_DEFINE_WATCHDOG_BINDER's function before the TU's first launch.
+static __device__ unsigned int* g_watchdog_ptr = nullptr;
+
+static __device__ __noinline__ void watchdog_report(unsigned int code) {
+  unsigned int* p = g_watchdog_ptr;
+  if (p) {
+    *reinterpret_cast<volatile unsigned int*>(p) = code;
+    __threadfence_system();
+  }
+}
+static __device__ __noinline__ void watchdog_trip(unsigned int code) {
+  watchdog_report(code);
+  __trap();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -66,8 +81,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {  // seconds; a healthy wait is microseconds
-      atomicExch(&g_watchdog_code, code);
-      __trap();
+      watchdog_trip(code);
     }
   }
 }
@@ -115,8 +129,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (++spins > (1u << 26)) {
-      atomicExch(&g_watchdog_code, code);
-      __trap();
+      watchdog_trip(code);
     }
   }
 }

@@ -416,15 +416,16 @@ static long long* g_trace_buf = nullptr;
 
 template <bool kTf32, int kEpi>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const GemmParams& p, int grid, cudaStream_t st) {
-  static bool configured[64] = {};  // per instantiation and device
+  static PerDeviceInit configured;  // per instantiation
   constexpr int smem = gemm_smem_bytes<kEpi>();
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  int rc = once_per_device(configured, [] {
     cudaError_t e = cudaFuncSetAttribute(tdnn_gemm_kernel<kTf32, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+    return static_cast<int>(XVEC_OK);
+  });
+  if (rc) return rc;
+  rc = bind_watchdog_gemm();
+  if (rc) return rc;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -529,7 +530,9 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
     y_dtype = XVEC_F32;
     y_ld = ws_ld;
   }
-  {
+  l2_policies(&p.pol_a, &p.pol_b, &p.pol_y);
+#ifdef XVEC_DEBUG
+  {  // developer instrumentation (XVEC_DBG epilogue/mainloop skip switches, XVEC_TRACE per-tile clock stamps): debug builds only
     static int dbg = -1;
     static long long* trace_buf = nullptr;
     if (dbg < 0) {
@@ -538,10 +541,10 @@ int gemm_dispatch(const void* x, int x_dtype, int64_t x_rows, int cin, int64_t x
       if (getenv("XVEC_TRACE")) cudaMalloc(&trace_buf, TRACE_TILES * TRACE_SLOTS * sizeof(long long));
     }
     p.dbg = dbg;
-    l2_policies(&p.pol_a, &p.pol_b, &p.pol_y);
     p.trace = trace_buf;
     g_trace_buf = trace_buf;
   }
+#endif
 
   CUtensorMap ta, tb, ty;
   // window form (x_ld < cin: overlapping rows): only rows whose whole window lies inside the matrix exist, the rest read as zero
@@ -590,11 +593,6 @@ int read_trace(long long* out_host, int n) {
   return m;
 }
 
-int read_watchdog() {
-  unsigned int v = 0;
-  cudaError_t e = cudaMemcpyFromSymbol(&v, g_watchdog_code, sizeof(v));
-  if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaMemcpyFromSymbol: %s", cudaGetErrorString(e));
-  return static_cast<int>(v);
-}
+XVEC_DEFINE_WATCHDOG_BINDER(bind_watchdog_gemm)
 
 }  // namespace xvec

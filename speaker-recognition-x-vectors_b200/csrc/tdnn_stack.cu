@@ -27,6 +27,8 @@
 #include "gemm_tile.cuh"
 #include <cuda_bf16.h>
 
+#include <mutex>
+
 namespace xvec {
 
 // Operand staging: the activation ("A") side is loaded once per 128-byte channel chunk as a SLAB of 128 + max_tap_offset frame
@@ -45,7 +47,7 @@ namespace xvec {
 constexpr int A_SLABS = XVEC_A_SLABS;
 constexpr int B_STAGES = XVEC_B_STAGES;
 constexpr int STACK_OUT_BUFS = XVEC_STACK_OUT_BUFS;  // store staging boxes (32 rows x 128 bytes) per epilogue warp
-constexpr int SLAB_ROWS_MAX = BM_CTA + 8;             // frame rows per slab (128 + the largest tap offset, <= 8)
+constexpr int SLAB_ROWS_MAX = BM_CTA + XVEC_STACK_MAX_TAP_OFFSET;  // frame rows per slab (128 + the largest tap offset, <= 8)
 constexpr int SLAB_BYTES = SLAB_ROWS_MAX * BK_BYTES;  // 17 KiB, a multiple of 1024
 static_assert(SLAB_BYTES % 1024 == 0, "slab bases must stay 1024-byte aligned for SWIZZLE_128B");
 constexpr int SCHED_SLOTS = 8;            // work-item ring between the scheduler and the warp roles
@@ -104,7 +106,10 @@ __host__ __device__ inline uint32_t decode_item(const StackParams& p, unsigned i
 }
 
 // Developer switches (-DXVEC_DEBUG builds only; XVEC_STACK_DBG): 1 skip the dependency waits, 2 skip the completion
-// signalling (only together with 1), 4 skip the proxy fences (results are then undefined; timing experiments only).
+// signalling (only together with 1 — alone it makes the dependency warps spin until the watchdog fires, which is what
+// tests/test_gpu_kernels.py::test_watchdog_code_is_readable uses), 4 skip the proxy fences (results are then undefined; timing
+// experiments only), 8 short watchdog limit for the dependency spin (2^12 polls instead of 2^24), 16 the dependency watchdog
+// reports its code and stops waiting instead of trapping (a trap is an Xid event on the box; the test only needs the code).
 // Debug builds also accumulate counters in the spare words of the control block (read by tools/stack_bench.py; units of 64
 // cycles unless stated): 1 tiles whose dependency warp had to spin on a flag (count), 2 flag polls (count), 3 producer waiting
 // for its dependency warp, 4 producer waiting for the work item, 5 MMA warp waiting for operands (explicit waits only),
@@ -361,9 +366,12 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         const unsigned* f = p.ready + static_cast<size_t>(layer - 1) * p.m_tiles + (mine ? mt + d : mt);
         uint32_t spins = 0;
         while (__any_sync(0xffffffffu, mine && ld_acquire_gpu_u32(f) < target)) {
-          if (++spins > (1u << 24)) {
-            atomicExch(&g_watchdog_code, 7u);
-            __trap();
+          if (++spins > (XVEC_SDBG(p, 8) ? (1u << 12) : (1u << 24))) {
+            if (XVEC_SDBG(p, 16)) {  // test mode: report, do not trap, stop waiting (the results are then garbage)
+              watchdog_report(7u);
+              break;
+            }
+            watchdog_trip(7u);
           }
         }
         XVEC_CNT(c_polls += spins; c_spun += spins ? 1 : 0;)
@@ -526,11 +534,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
 //     which saves the HBM round trip of every activation and the power that goes with it — the kernel runs at the 1000 W cap,
 //     so this is throughput: one band 294 / 336 us (burst / sustained), bands of 160-170: 278 / 322 us, 180-200: 282-284 /
 //     326-328 us, 225: 292 / 332 us, 250: 311 / 347 us.  64 x 6000 frames (1500 m-tiles): 1474 -> 1382 us; 437 x 300: 519 -> 467 us.
-// Hence equal bands of about 2.3 x pairs m-tiles.  XVEC_BAND overrides (developer A/B switch).
-static int pick_band(int m_tiles, int n_layers, int pairs) {
-  const char* e = getenv("XVEC_BAND");
-  const int env = e ? atoi(e) : 0;
-  int band = env;
+// Hence equal bands of about 2.3 x pairs m-tiles.  `want` > 0 (xvec_tdnn_stack's band argument; tests and tools) overrides.
+static int pick_band(int m_tiles, int n_layers, int pairs, int want) {
+  int band = want;
   if (band <= 0) {
     // equal bands of about 2.3 x pairs m-tiles: a short last band runs its five layers as a serial chain of a few tiles each
     // (437 x 300 frames = 512 m-tiles: bands 170+170+170+6 take 525 us, 3 x 172 take 487 us)
@@ -576,7 +582,7 @@ int64_t stack_plan(int64_t rows, int n_layers, const int32_t* n_tiles_per_layer,
     if (n_tiles_per_layer[l] < 1 || n_tiles_per_layer[l] > 31) return set_error(XVEC_E_ARG, "bad n_tiles");
     p.L[l].n_tiles = n_tiles_per_layer[l];
   }
-  int rc = fill_schedule(p, band > 0 ? band : pick_band(p.m_tiles, n_layers, 74));
+  int rc = fill_schedule(p, pick_band(p.m_tiles, n_layers, 74, band));
   if (rc) return rc;
   if (items_out) {
     int cursor = 0;
@@ -591,17 +597,20 @@ int64_t stack_ctrl_bytes(int64_t rows, int n_layers) {
   return 128 + (n_layers - 1) * m_tiles * 4;
 }
 
+XVEC_DEFINE_WATCHDOG_BINDER(bind_watchdog_stack)
+
 template <bool kAllTf32>
 static int launch_stack(const StackMaps& maps, const StackParams& p, int grid, cudaStream_t st) {
-  static bool configured[64] = {};
+  static PerDeviceInit configured;  // per instantiation
   constexpr int smem = stack_smem_bytes();
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  int rc = once_per_device(configured, [] {
     cudaError_t e = cudaFuncSetAttribute(tdnn_stack_kernel<kAllTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
+    return static_cast<int>(XVEC_OK);
+  });
+  if (rc) return rc;
+  rc = bind_watchdog_stack();
+  if (rc) return rc;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(STACK_THREADS);
@@ -637,19 +646,37 @@ bool stack_supported(const XvecLayerDesc* tdnn, int n_tdnn, int64_t rows) {
   return true;
 }
 
-int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t rows, int64_t x_ld, void* act0, void* act1,
-                   int64_t act_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part, void* ctrl, int64_t ctrl_bytes,
-                   void* stream) {
-  int rc = device_check();
-  if (rc) return rc;
-  if (!stack_supported(tdnn, n_tdnn, rows)) return set_error(XVEC_E_ARG, "layer stack is not supported by the fused stack kernel");
-  if (!x || !act0 || !act1 || !row_utt || !blk_slot_base || !part || !ctrl) return set_error(XVEC_E_ARG, "null pointer argument");
-  if (ctrl_bytes < stack_ctrl_bytes(rows, n_tdnn) || (reinterpret_cast<uintptr_t>(ctrl) & 127u))
-    return set_error(XVEC_E_ARG, "ctrl_dev must be 128-byte aligned and hold xvec_stack_ctrl_bytes() bytes");
-  const bool all_tf32 = tdnn[1].dtype == XVEC_F32;
+// Everything stack_dispatch derives from its arguments except the per-call pointers: the 3 x n_layers tensor maps (a
+// cuTensorMapEncodeTiled each — together most of the host time of a call) and the kernel parameters.  A pipeline calls with
+// the same few (input, scratch, weights, rows) combinations over and over — one per slot — so the last STACK_PLAN_CACHE of
+// them are kept, keyed by every argument a map or a parameter depends on.  A key describes pointers AND extents, so an entry
+// stays valid for as long as its key can recur.
+struct StackKey {
+  int dev, n_tdnn, band;
+  int64_t rows, x_ld, act_ld;
+  const void *x, *act0, *act1;
+  XvecLayerDesc L[XVEC_MAX_STACK];
+};
+struct StackPlan {
+  StackKey key;
+  StackMaps maps;
+  StackParams p;
+  int grid;
+  bool all_tf32;
+  uint64_t stamp;  // 0 = empty
+};
+constexpr int STACK_PLAN_CACHE = 64;
+static std::mutex g_plan_mu;
+static StackPlan g_plans[STACK_PLAN_CACHE];
+static uint64_t g_plan_clock = 0;
+
+static int build_plan(StackPlan& pl, const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t rows, int64_t x_ld, void* act0, void* act1,
+                      int64_t act_ld, int band) {
+  pl.all_tf32 = tdnn[1].dtype == XVEC_F32;
   const int act_dtype = tdnn[1].dtype;
-  StackMaps local_maps;
-  StackParams p{};
+  StackMaps& maps = pl.maps;
+  StackParams& p = pl.p;
+  p = StackParams{};
   p.rows = static_cast<int>(rows);
   p.m_tiles = static_cast<int>((rows + BM - 1) / BM);
   p.n_layers = n_tdnn;
@@ -657,6 +684,7 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
   const void* h = x;
   int64_t h_ld = x_ld;
   int h_dtype = tdnn[0].dtype;
+  int rc;
   for (int l = 0; l < n_tdnn; ++l) {
     const XvecLayerDesc& d = tdnn[l];
     StackLayer& L = p.L[l];
@@ -677,57 +705,119 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
     // window form (h_ld < cin: overlapping rows): only rows whose whole window lies inside the matrix exist, the rest read as zero
     const int64_t h_rows = h_ld < d.cin ? rows - (d.cin + h_ld - 1) / h_ld + 1 : rows;
     if (h_rows <= 0) return set_error(XVEC_E_ARG, "window form: fewer rows than one window");
-    rc = make_tmap_2d(&local_maps.a[l], h, h_dtype, static_cast<uint64_t>(d.cin), static_cast<uint64_t>(h_rows), static_cast<uint64_t>(h_ld),
+    rc = make_tmap_2d(&maps.a[l], h, h_dtype, static_cast<uint64_t>(d.cin), static_cast<uint64_t>(h_rows), static_cast<uint64_t>(h_ld),
                       bke, static_cast<uint32_t>(L.slab_rows));
     if (rc) return rc;
     // packed weights are chunk-major (xvec_pack_weight): a (kblocks * n_pad) x bke matrix, one contiguous 16 KiB box per load
     const uint64_t n_pad = static_cast<uint64_t>(L.n_tiles) * BN;
     L.n_pad = static_cast<int>(n_pad);
-    rc = make_tmap_2d(&local_maps.b[l], d.w_packed_dev, d.dtype, bke, static_cast<uint64_t>(d.taps) * L.cpt * n_pad, bke, bke, BN_CTA);
+    rc = make_tmap_2d(&maps.b[l], d.w_packed_dev, d.dtype, bke, static_cast<uint64_t>(d.taps) * L.cpt * n_pad, bke, bke, BN_CTA);
     if (rc) return rc;
     if (l + 1 < n_tdnn) {
       // store boxes: 32 rows x 32 columns (64-byte rows / SWIZZLE_64B for bf16, 128-byte rows / SWIZZLE_128B for float32)
-      rc = make_tmap_2d(&local_maps.y[l], act[l & 1], act_dtype, static_cast<uint64_t>(d.n), static_cast<uint64_t>(rows),
+      rc = make_tmap_2d(&maps.y[l], act[l & 1], act_dtype, static_cast<uint64_t>(d.n), static_cast<uint64_t>(rows),
                         static_cast<uint64_t>(act_ld), 32, 32, act_dtype == XVEC_BF16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
       h = act[l & 1];
       h_ld = act_ld;
       h_dtype = act_dtype;
     } else {
-      local_maps.y[l] = local_maps.a[l];  // unused
+      maps.y[l] = maps.a[l];  // unused
     }
   }
   for (int l = n_tdnn; l < XVEC_MAX_STACK; ++l) {
-    local_maps.a[l] = local_maps.a[0];
-    local_maps.b[l] = local_maps.b[0];
-    local_maps.y[l] = local_maps.a[0];
+    maps.a[l] = maps.a[0];
+    maps.b[l] = maps.b[0];
+    maps.y[l] = maps.a[0];
   }
   const int max_pairs = num_sms() / 2;
-  rc = fill_schedule(p, pick_band(p.m_tiles, n_tdnn, max_pairs));
+  rc = fill_schedule(p, pick_band(p.m_tiles, n_tdnn, max_pairs, band));
   if (rc) return rc;
-  const unsigned acc = p.total_items;
-  p.counter = static_cast<unsigned*>(ctrl);
-  p.ready = reinterpret_cast<unsigned*>(static_cast<char*>(ctrl) + 128);
-  p.row_utt = row_utt;
-  p.blk_slot_base = blk_slot_base;
-  p.part = part;
   l2_policies(&p.pol_a, &p.pol_b, &p.pol_y);
-  {
-    const char* e = getenv("XVEC_STACK_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(ctrl, 0, static_cast<size_t>(stack_ctrl_bytes(rows, n_tdnn)), st);
-  if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaMemsetAsync(ctrl): %s", cudaGetErrorString(e));
-  int64_t pairs = static_cast<int64_t>(acc) < max_pairs ? acc : max_pairs;
+  int64_t pairs = static_cast<int64_t>(p.total_items) < max_pairs ? p.total_items : max_pairs;
 #ifdef XVEC_DEBUG
   if (const char* e = getenv("XVEC_STACK_PAIRS")) {  // experiment: fewer CTA pairs (is the operand stream a per-SM or a global limit?)
     const int v = atoi(e);
     if (v > 0 && v < pairs) pairs = v;
   }
 #endif
-  const int grid = 2 * static_cast<int>(pairs);
-  return all_tf32 ? launch_stack<true>(local_maps, p, grid, st) : launch_stack<false>(local_maps, p, grid, st);
+  pl.grid = 2 * static_cast<int>(pairs);
+  return XVEC_OK;
+}
+
+int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t rows, int64_t x_ld, void* act0, void* act1,
+                   int64_t act_ld, const int32_t* row_utt, const int32_t* blk_slot_base, float* part, void* ctrl, int64_t ctrl_bytes,
+                   int band, void* stream) {
+  int rc = device_check();
+  if (rc) return rc;
+  if (!stack_supported(tdnn, n_tdnn, rows)) return set_error(XVEC_E_ARG, "layer stack is not supported by the fused stack kernel");
+  if (!x || !act0 || !act1 || !row_utt || !blk_slot_base || !part || !ctrl) return set_error(XVEC_E_ARG, "null pointer argument");
+  if (ctrl_bytes < stack_ctrl_bytes(rows, n_tdnn) || (reinterpret_cast<uintptr_t>(ctrl) & 127u))
+    return set_error(XVEC_E_ARG, "ctrl_dev must be 128-byte aligned and hold xvec_stack_ctrl_bytes() bytes");
+  StackKey key;
+  memset(&key, 0, sizeof(key));  // padding bytes too: keys are compared with memcmp
+  cudaGetDevice(&key.dev);
+  key.n_tdnn = n_tdnn;
+  key.band = band > 0 ? band : 0;
+  key.rows = rows;
+  key.x_ld = x_ld;
+  key.act_ld = act_ld;
+  key.x = x;
+  key.act0 = act0;
+  key.act1 = act1;
+  for (int l = 0; l < n_tdnn; ++l) {
+    XvecLayerDesc& k = key.L[l];  // field by field: the caller's struct may carry garbage in unused tap slots
+    k.w_packed_dev = tdnn[l].w_packed_dev;
+    k.bias_dev = tdnn[l].bias_dev;
+    k.n = tdnn[l].n;
+    k.cin = tdnn[l].cin;
+    k.taps = tdnn[l].taps;
+    k.dtype = tdnn[l].dtype;
+    for (int j = 0; j < tdnn[l].taps; ++j) k.tap_offsets[j] = tdnn[l].tap_offsets[j];
+  }
+  StackMaps maps;
+  StackParams p;
+  int grid;
+  bool all_tf32;
+  {
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    StackPlan* hit = nullptr;
+    StackPlan* victim = &g_plans[0];
+    for (StackPlan& pl : g_plans) {
+      if (pl.stamp && memcmp(&pl.key, &key, sizeof(key)) == 0) {
+        hit = &pl;
+        break;
+      }
+      if (pl.stamp < victim->stamp) victim = &pl;
+    }
+    if (!hit) {
+      victim->stamp = 0;
+      rc = build_plan(*victim, tdnn, n_tdnn, x, rows, x_ld, act0, act1, act_ld, band);
+      if (rc) return rc;
+      victim->key = key;
+      hit = victim;
+    }
+    hit->stamp = ++g_plan_clock;
+    maps = hit->maps;
+    p = hit->p;
+    grid = hit->grid;
+    all_tf32 = hit->all_tf32;
+  }
+  p.counter = static_cast<unsigned*>(ctrl);
+  p.ready = reinterpret_cast<unsigned*>(static_cast<char*>(ctrl) + 128);
+  p.row_utt = row_utt;
+  p.blk_slot_base = blk_slot_base;
+  p.part = part;
+#ifdef XVEC_DEBUG
+  {
+    const char* e = getenv("XVEC_STACK_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+#endif
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(ctrl, 0, static_cast<size_t>(stack_ctrl_bytes(rows, n_tdnn)), st);
+  if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaMemsetAsync(ctrl): %s", cudaGetErrorString(e));
+  return all_tf32 ? launch_stack<true>(maps, p, grid, st) : launch_stack<false>(maps, p, grid, st);
 }
 
 }  // namespace xvec

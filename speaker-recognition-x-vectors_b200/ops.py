@@ -108,9 +108,10 @@ def tdnn_pool_fused(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
 
 
 def tdnn_stack(layer_descs, n_layers: int, x: torch.Tensor, act0: torch.Tensor, act1: torch.Tensor, row_utt: torch.Tensor,
-               blk_slot_base: torch.Tensor, part: torch.Tensor, ctrl: torch.Tensor):
+               blk_slot_base: torch.Tensor, part: torch.Tensor, ctrl: torch.Tensor, band: int = 0):
     """All TDNN layers of the stack in one persistent launch (xvec_tdnn_stack): layers 0..n-2 ping-pong through act0/act1,
-    the last one fills the pooling partials `part`.  layer_descs: ctypes array of _lib.LayerDesc (packed operands)."""
+    the last one fills the pooling partials `part`.  layer_descs: ctypes array of _lib.LayerDesc (packed operands);
+    band: m-tiles per scheduling band (0 = the library's choice; every value gives the same bits)."""
     _require_cuda(x, act0, act1, row_utt, blk_slot_base, part, ctrl)
     lib = _lib.load()
     x_ld = _rowmajor_2d(x, "x")
@@ -124,14 +125,17 @@ def tdnn_stack(layer_descs, n_layers: int, x: torch.Tensor, act0: torch.Tensor, 
         raise ValueError("pooling bookkeeping arrays are too small for this frame matrix")
     with torch.cuda.device(x.device):
         check(lib.xvec_tdnn_stack(layer_descs, n_layers, ptr(x), rows, x_ld, ptr(act0), ptr(act1), act_ld, ptr(row_utt), ptr(blk_slot_base),
-                                  ptr(part), ptr(ctrl), ctrl.numel(), stream_ptr()))
+                                  ptr(part), ptr(ctrl), ctrl.numel(), int(band), stream_ptr()))
     return part
 
 
 def pool_finalize(part: torch.Tensor, slot_start: torch.Tensor, n_rows: torch.Tensor, p: int, bn_scale=None, bn_shift=None,
-                  out: torch.Tensor | None = None, out_lp: torch.Tensor | None = None):
-    """[mean || unbiased std] per utterance from partial sums; returns float32 (n_utts, 2p)."""
-    _require_cuda(part, slot_start, n_rows, bn_scale, bn_shift, out, out_lp)
+                  out: torch.Tensor | None = None, out_lp: torch.Tensor | None = None, pivot: torch.Tensor | None = None):
+    """[mean || unbiased std] per utterance from partial sums; returns float32 (n_utts, 2p).  pivot: float32 (n_utts, p) when
+    the partial sums were taken of x - pivot (stats_pool_ragged)."""
+    _require_cuda(part, slot_start, n_rows, bn_scale, bn_shift, out, out_lp, pivot)
+    if pivot is not None and (pivot.dtype != torch.float32 or not pivot.is_contiguous() or pivot.shape != (n_rows.numel(), p)):
+        raise ValueError("pivot must be contiguous float32 (n_utts, p)")
     lib = _lib.load()
     n_utts = n_rows.numel()
     if out is None:
@@ -143,7 +147,7 @@ def pool_finalize(part: torch.Tensor, slot_start: torch.Tensor, n_rows: torch.Te
         lp_ld = _rowmajor_2d(out_lp, "out_lp")
         lp_code = dtype_code(out_lp.dtype)
     with torch.cuda.device(part.device):
-        check(lib.xvec_pool_finalize(ptr(part), ptr(slot_start), ptr(n_rows), n_utts, p, ptr(bn_scale), ptr(bn_shift), ptr(out),
+        check(lib.xvec_pool_finalize(ptr(part), ptr(slot_start), ptr(n_rows), n_utts, p, ptr(bn_scale), ptr(bn_shift), ptr(pivot), ptr(out),
                                      ptr(out_lp), lp_code, lp_ld, stream_ptr()))
     return out
 
@@ -187,10 +191,11 @@ def stats_pool_ragged(x: torch.Tensor, row_start: np.ndarray, n_rows: np.ndarray
         _POOL_LAYOUTS[key] = hit
     rs_d, nr_d, ss_d, n_slots, max_chunks = hit
     part = torch.empty((n_slots, 2, p), dtype=torch.float32, device=dev)
+    pivot = torch.empty((len(n_rows), p), dtype=torch.float32, device=dev)  # each utterance's first row: the sums are shifted by it
     with torch.cuda.device(dev):
         check(lib.xvec_stats_pool_partial(ptr(x), dtype_code(x.dtype), ld, p, ptr(rs_d), ptr(nr_d), ptr(ss_d), len(n_rows),
-                                          max_chunks, ptr(part), stream_ptr()))
-    return pool_finalize(part, ss_d, nr_d, p, out_lp=out_lp)
+                                          max_chunks, ptr(part), ptr(pivot), stream_ptr()))
+    return pool_finalize(part, ss_d, nr_d, p, out_lp=out_lp, pivot=pivot)
 
 
 def mfcc(wav: torch.Tensor, wav_lengths, normalize: bool = True, out: torch.Tensor | None = None):

@@ -57,6 +57,9 @@ class TdnnLayer(nn.Module):
         hit = self._prep.get(dtype)
         if hit is not None and hit[0] == fp:
             return hit[1]
+        if hit is not None and hit[1][0].is_cuda:  # operands about to be dropped may still be read by kernels in flight
+            with torch.cuda.device(hit[1][0].device):
+                torch.cuda.synchronize()
         offs = tap_offsets(self.context)
         w = ops.pack_weight(self.linear.weight, len(offs), self.input_size, dtype)
         bias = ops.pad32(self.linear.bias)
@@ -70,6 +73,9 @@ class TdnnLayer(nn.Module):
             shift = ops.pad32((beta - n.running_mean.detach().double() * s).float())
         out = (w, bias, scale, shift)
         self._prep[dtype] = (fp, out)
+        if w.is_cuda:  # the cached operands may be used from any stream from here on (see xvector._prep_fence)
+            with torch.cuda.device(w.device):
+                torch.cuda.current_stream().synchronize()
         return out
 
     def bn_affine64(self):

@@ -23,7 +23,25 @@ from . import _lib, ops
 from .layout import utterance_layout
 from .tdnn_layer import TdnnLayer, _aligned_rows, tap_offsets
 
+# "tf32": float32 storage, tensor-core math in TF32 (10-bit mantissa operands, fp32 accumulate; measured 1e-4 of the row norm
+# against the reference's fp32, bound 1e-3).  "fp32" is kept as an alias for callers that name the reference's dtype
+# (main.py:137 samples.float()); it is the SAME TF32 arithmetic, not IEEE fp32 products.  "bf16": bfloat16 activations/weights.
 PRECISIONS = {"tf32": torch.float32, "fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+def _prep_fence(device, drain_all: bool):
+    """Parameter preparation (float64 BN fold, weight packing, casts) is enqueued on whatever stream is current and its
+    results are cached and then read by kernels on OTHER streams (one per pipeline slot) with no event in between.  Make the
+    hand-over explicit: block the host until the preparing stream is done (drain_all=False, after building), or until every
+    stream of the device is idle (drain_all=True, before dropping operands that kernels in flight may still read).  Runs
+    once per parameter change, never per batch."""
+    if device.type != "cuda":
+        return
+    with torch.cuda.device(device):
+        if drain_all:
+            torch.cuda.synchronize()
+        else:
+            torch.cuda.current_stream().synchronize()
 
 
 class _Layout:
@@ -189,7 +207,7 @@ class XVectorModel(nn.Module):
         return (2 <= len(layers) <= _lib.MAX_STACK
                 and all(l.output_size % _lib.TILE_N == 0 for l in layers[:-1])
                 and all(a.output_size == b.input_size for a, b in zip(layers[:-1], layers[1:]))
-                and all(tap_offsets(l.context)[-1] <= 128 for l in layers))
+                and all(tap_offsets(l.context)[-1] <= _lib.STACK_MAX_TAP_OFFSET for l in layers))
 
     def _stack_params(self):
         """Packed operands of the five TDNN layers for the fused pipeline, with every layer's eval-mode BatchNorm folded
@@ -203,6 +221,8 @@ class XVectorModel(nn.Module):
         hit = self._fc_prep.get("stack")
         if hit is not None and hit[0] == fp:
             return hit[1]
+        if hit is not None:
+            _prep_fence(self._device(), drain_all=True)  # kernels in flight may still read the operands about to be dropped
         out, prev = [], None
         for i, layer in enumerate(layers):
             layer._check_eval()
@@ -220,6 +240,7 @@ class XVectorModel(nn.Module):
         last_bn = (None, None) if prev is None else (prev[0].float().contiguous(), prev[1].float().contiguous())
         res = (out, last_bn)
         self._fc_prep["stack"] = (fp, res)
+        _prep_fence(self._device(), drain_all=False)
         return res
 
     def _pipeline(self):
@@ -232,6 +253,8 @@ class XVectorModel(nn.Module):
         hit = self._fc_prep.get("pipeline")
         if hit is not None and hit[0] == fp:
             return hit[1]
+        if hit is not None:
+            _prep_fence(self._device(), drain_all=True)
         stack, (scale5, shift5) = self._stack_params()
         code = _lib.dtype_code
         tdnn = (_lib.LayerDesc * len(layers))()
@@ -271,6 +294,7 @@ class XVectorModel(nn.Module):
                "scale5": scale5, "shift5": shift5, "out_dim": fcs[-1].out_features, "hidden": fcs[0].out_features,
                "fc_shapes": [(f.in_features, f.out_features) for f in fcs]}
         self._fc_prep["pipeline"] = (fp, res)
+        _prep_fence(self._device(), drain_all=False)  # every slot's stream may use the operands from here on
         return res
 
     def _fc(self, lin: nn.Linear, dtype):
@@ -278,9 +302,12 @@ class XVectorModel(nn.Module):
         hit = self._fc_prep.get((id(lin), dtype))
         if hit is not None and hit[0] == fp:
             return hit[1]
+        if hit is not None:
+            _prep_fence(lin.weight.device, drain_all=True)
         w = ops.pack_weight(lin.weight, 1, lin.in_features, dtype)
         b = ops.pad32(lin.bias)
         self._fc_prep[(id(lin), dtype)] = (fp, (w, b))
+        _prep_fence(lin.weight.device, drain_all=False)
         return w, b
 
     def _linear(self, lin: nn.Linear, x2d: torch.Tensor, relu: bool, out_dtype) -> torch.Tensor:
@@ -290,6 +317,16 @@ class XVectorModel(nn.Module):
             self._fc_prep[key] = ops.splitk_workspace(x2d.shape[0], lin.in_features, 1, lin.out_features, x2d.dtype, x2d.device)
         return ops.tdnn_layer_flat(x2d, w, lin.out_features, [0], b, None, None, relu=relu, out_dtype=out_dtype, cin=lin.in_features,
                                    workspace=self._fc_prep[key])
+
+    def _frames_for(self, flat_x: torch.Tensor, pipe) -> torch.Tensor:
+        """The frame matrix as layer 1 reads it: 16-byte aligned rows, and DENSE rows (stride == input_size) when layer 1 is in
+        window form — its taps*cin window is one contiguous run only then (include/xvec_b200.h, xvec_tdnn_stack).  A (rows, 24)
+        view of a wider buffer (ops.mfcc(out=...) allows one) is copied once instead of silently mixing padding columns into the
+        taps."""
+        x = _aligned_rows(flat_x)
+        if pipe["window"] is not None and x.stride(0) != self.input_size:
+            x = _aligned_rows(x.contiguous())
+        return x
 
     # ------------------------------------------------------------------ the hot path
     def pooled_stats_flat(self, flat_x: torch.Tensor, lengths, slot: int = 0) -> "tuple[torch.Tensor, torch.Tensor | None]":
@@ -313,7 +350,7 @@ class XVectorModel(nn.Module):
         part = sc.part[: lay.n_slots]
         pooled = sc.pooled[: lay.n_utts]
         pooled_lp = None if sc.pooled_lp is None else sc.pooled_lp[: lay.n_utts]
-        x = _aligned_rows(flat_x)  # layer 1 always reads the float32 frames (TF32 math): no cast pass over the input
+        x = self._frames_for(flat_x, pipe)  # layer 1 always reads the float32 frames (TF32 math): no cast pass over the input
         if self._stack_kernel_ok():
             ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], x, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
         else:  # layer widths the one-launch stack kernel does not take: one launch per layer
@@ -356,7 +393,7 @@ class XVectorModel(nn.Module):
         sc.ensure_head(lay.n_utts, pipe["fc_shapes"], pipe["hidden"])
         if flat_x.dtype != torch.float32:
             flat_x = flat_x.float()
-        x = _aligned_rows(flat_x)
+        x = self._frames_for(flat_x, pipe)
         out = torch.empty((lay.n_utts, pipe["out_dim"]), dtype=torch.float32, device=flat_x.device)
         lib = _lib.load()
         p = _lib.ptr
@@ -411,9 +448,22 @@ class XVectorModel(nn.Module):
         x_vecs = self.extract_x_vec(samples.float())
         return [(x_vecs, labels, ids)]
 
-    def load_reference_checkpoint(self, path: str, map_location="cpu"):
-        """Load the 'state_dict' of a Lightning checkpoint written by the reference (main.py:198,213)."""
-        ckpt = torch.load(path, map_location=map_location, weights_only=False)
-        sd = ckpt.get("state_dict", ckpt)
-        own = set(self.state_dict().keys())
+    def load_reference_checkpoint(self, path: str, map_location="cpu", trust_pickle: bool = False):
+        """Load the 'state_dict' of a Lightning checkpoint written by the reference (main.py:198,213).
+        The file is read with torch.load(weights_only=True); a checkpoint that also pickles Lightning objects (callback state,
+        hyper-parameter containers) needs the full unpickler, which executes code from the file — that is only done on
+        explicit opt-in (trust_pickle=True, for files you wrote yourself).  Keys this model does not have (the reference's
+        metric modules) are ignored; a key this model HAS and the checkpoint lacks is an error, not a silent random init."""
+        try:
+            ckpt = torch.load(path, map_location=map_location, weights_only=True)
+        except Exception as e:
+            if not trust_pickle:
+                raise RuntimeError(f"{path} cannot be read with weights_only=True ({type(e).__name__}: {e}); pass trust_pickle=True "
+                                   "only for a checkpoint from a trusted source") from e
+            ckpt = torch.load(path, map_location=map_location, weights_only=False)
+        sd = ckpt.get("state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
+        own = self.state_dict()
+        missing = [k for k in own if k not in sd and not k.endswith("num_batches_tracked")]
+        if missing:
+            raise KeyError(f"checkpoint lacks {len(missing)} parameter(s) of the x-vector model, e.g. {missing[:3]}")
         return self.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)

@@ -3,6 +3,8 @@
 Tolerances (north_star): TF32 path max-abs error <= 1e-3 relative to the norm of the reference row;
 bf16 path cosine >= 0.9999 per row.  Integer / layout logic is exact.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -127,6 +129,21 @@ def test_stats_pool_standalone(xb, dtype):
             assert torch.isnan(out[u, 1500:]).all()   # torch.std of one frame is NaN (main.py:61)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stats_pool_large_mean_small_std(xb, dtype):
+    """|mean| >> std: a one-pass float32 sum of squares loses the variance (1e4 * 2^-24 per term against a variance of 1); the
+    kernel sums x - (first row) instead.  torch.std (main.py:61) is two-pass, so the public stat_pool surface must hold 1e-4 here."""
+    g = torch.Generator().manual_seed(6)
+    x = (100.0 + torch.randn(7, 900, 1500, generator=g)).cuda().to(dtype)
+    x[3] -= 250.0  # a negative mean as well
+    m = xb.XVectorModel().cuda().eval()
+    got = m.stat_pool(x).double()
+    xd = x.double()
+    ref = torch.cat((xd.mean(1), xd.std(1)), 1)
+    assert torch.allclose(got[:, :1500], ref[:, :1500], rtol=1e-6, atol=1e-5)
+    assert ((got[:, 1500:] - ref[:, 1500:]).abs() / ref[:, 1500:]).max().item() < 1e-4
+
+
 def test_stat_pool_module_surface(xb, state_dict):
     m = xb.XVectorModel().cuda().eval()
     x = torch.randn(5, 61, 1500, device="cuda")
@@ -233,12 +250,10 @@ def test_stack_kernel_equals_per_layer_launches(xb, state_dict, precision, band,
     w, bias, offs = stack[-1]
     part_ref = torch.zeros((lay.n_slots, 2, 1500), device="cuda")
     ops.tdnn_pool_fused(h, w, 1500, offs, bias, lay.row_utt, lay.blk_slot_base, part_ref)
-    if band:
-        monkeypatch.setenv("XVEC_BAND", str(band))
     for rep in range(3):  # repeated launches reuse (and re-zero) the same control block
         part = torch.zeros((lay.n_slots, 2, 1500), device="cuda")
         sc.act[0].zero_(); sc.act[1].zero_()
-        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, band=band)
         torch.cuda.synchronize()
         assert torch.equal(part, part_ref)
         # layer 3 / layer 4 outputs are what is left in the ping-pong buffers
@@ -268,14 +283,12 @@ def test_stack_kernel_two_launches_in_flight(xb, state_dict, monkeypatch):
     torch.cuda.synchronize()
     streams = [torch.cuda.Stream() for _ in range(2)]
     for band in (0, 7):
-        if band:
-            monkeypatch.setenv("XVEC_BAND", str(band))
         parts = [[torch.zeros_like(ref) for _ in range(4)] for _ in range(2)]
         for rep in range(4):
             for s in range(2):
                 with torch.cuda.stream(streams[s]):
                     ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs[s][0], scs[s].act[0], scs[s].act[1], lay.row_utt, lay.blk_slot_base,
-                                   parts[s][rep], scs[s].ctrl)
+                                   parts[s][rep], scs[s].ctrl, band=band)
         torch.cuda.synchronize()
         assert all(torch.equal(pt, ref) for ps in parts for pt in ps)
     assert xb._lib.load().xvec_watchdog_code() == 0
@@ -301,3 +314,39 @@ def test_linear_small_matches_reference(xb, dtype, rows, k, n, relu, out_dtype):
     assert ((got - ref).abs().max() / ref.abs().max()).item() < tol
     with pytest.raises(Exception):
         xb.ops.linear_small(x[:, :-3].contiguous().cuda(), W[:, :-3].contiguous().cuda())  # k not a multiple of 16 bytes
+
+
+def test_watchdog_code_is_readable():
+    """A protocol failure inside the stack kernel must leave a readable code.  The debug library (-DXVEC_DEBUG) can be told to skip
+    the completion signalling (XVEC_STACK_DBG bit 2) with a short spin limit (bit 8) and a watchdog that reports without trapping
+    (bit 16; a real trap is an Xid event and destroys the context): the dependency warps then give up with code 7.  The code is
+    read back from the mapped host word — it used to live in a per-translation-unit __device__ variable that the reader, in
+    another unit, never saw.  Child process: the parent has already loaded the product library."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dbg_lib = os.path.join(root, "speaker-recognition-x-vectors_b200", "libxvec_b200_debug.so")
+    if not os.path.exists(dbg_lib):
+        import importlib
+        importlib.import_module("speaker-recognition-x-vectors_b200.build").build(debug=True)
+    child = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import xvec_b200
+lib = xvec_b200._lib.load()
+m = xvec_b200.XVectorModel(precision="bf16").cuda().eval()
+x = torch.randn(4, 200, 24, device="cuda")
+assert lib.xvec_watchdog_code() == 0
+m.extract_x_vec(x)
+torch.cuda.synchronize()
+code = lib.xvec_watchdog_code()
+lib.xvec_watchdog_reset()
+print("watchdog", code, "after reset", lib.xvec_watchdog_code(), flush=True)
+""" % root
+    env = dict(os.environ, XVEC_LIB=dbg_lib, XVEC_STACK_DBG="26")
+    r = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=300)
+    assert "watchdog 7 after reset 0" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    # ... and the same child with the switches off runs clean
+    env = dict(os.environ, XVEC_LIB=dbg_lib, XVEC_STACK_DBG="0")
+    r = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=300)
+    assert "watchdog 0 after reset 0" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

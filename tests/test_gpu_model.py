@@ -191,3 +191,71 @@ def test_plda_trial_scores_and_decisions(xb):
     assert abs(scoring.eer(got, target)[0] - scoring.eer(ref, target)[0]) < 1e-9
     with pytest.raises(ValueError):
         sc.score_trials(torch.zeros(4, 100).cuda(), [0], [1])
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_strided_frame_matrix_is_not_read_as_windows(xb, state_dict, precision):
+    """A (rows, 24) view of a wider buffer (what ops.mfcc(out=...) may hand over): TDNN1's window form is only valid on dense
+    rows, so the model must not describe this input as overlapping 120-value windows (it would mix the padding columns into the
+    taps).  Same bits as the dense copy, and parity with the oracle."""
+    m = _model(xb, state_dict, precision)
+    lens = np.asarray([120, 45, 300, 77])
+    utts = ox.synth_ragged(lens, seed=91)
+    dense = torch.cat(utts).cuda()
+    wide = torch.full((dense.shape[0], 32), 1e6, device="cuda")  # poison in the padding columns
+    wide[:, :24] = dense
+    view = wide[:, :24]
+    assert view.stride(0) == 32
+    a = m.extract_x_vec_flat(view, lens).clone()
+    b = m.extract_x_vec_flat(dense, lens).clone()
+    assert torch.equal(a, b)
+    pa, _ = m.pooled_stats_flat(view, lens)
+    pa = pa.clone()
+    pb, _ = m.pooled_stats_flat(dense, lens)
+    assert torch.equal(pa, pb)
+    ref = ox.extract_ragged_t(state_dict, utts, 6).numpy()
+    got = a.cpu().numpy()
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    assert cos.min() > 0.9999
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_wide_context_falls_back_to_per_layer_launches(xb, precision):
+    """A stack the one-launch kernel does not take (tap span 10 > XVEC_STACK_MAX_TAP_OFFSET = 8): extract_x_vec_flat (C-side
+    fallback) and pooled_stats_flat / forward (Python-side fallback) must both run it one launch per layer, and agree with a
+    plain torch fp32 statement of the reference's op sequence (tdnn_layer.py:26-41, main.py:59-63, 81-94)."""
+    torch.manual_seed(3)
+    m = xb.XVectorModel(precision=precision)
+    m.time_context_layers[1] = xb.TdnnLayer(input_size=512, output_size=512, context=[-5, 0, 5])
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for layer in m.time_context_layers:
+            layer.norm.running_mean.copy_(0.3 * torch.randn(layer.norm.num_features, generator=g))
+            layer.norm.running_var.copy_(0.5 + torch.rand(layer.norm.num_features, generator=g))
+    m = m.cuda().eval()
+    assert not m._stack_kernel_ok() and m.lost_frames == 4 + 10 + 6
+    x = torch.randn(3, 90, 24, generator=g)
+
+    def ref_forward(x):
+        h = x.double()
+        for layer in m.time_context_layers:
+            offs = xb.tap_offsets(layer.context)
+            t_out = h.shape[1] - offs[-1]
+            u = torch.cat([h[:, o:o + t_out] for o in offs], 2)
+            h = torch.relu(u @ layer.linear.weight.double().cpu().t() + layer.linear.bias.double().cpu())
+            n = layer.norm
+            h = (h - n.running_mean.double().cpu()) / torch.sqrt(n.running_var.double().cpu() + n.eps) * n.weight.double().cpu() + n.bias.double().cpu()
+        pooled = torch.cat((h.mean(1), h.std(1)), 1)
+        return pooled, pooled @ m.segment_layer6.weight.double().cpu().t() + m.segment_layer6.bias.double().cpu()
+
+    with torch.no_grad():
+        pooled_ref, xv_ref = ref_forward(x)
+    got = m.extract_x_vec(x.cuda()).double().cpu()
+    pooled, _ = m.pooled_stats_flat(x.reshape(-1, 24).cuda(), [90] * 3)
+    pooled = pooled.double().cpu()
+    tol = 1e-3 if precision == "tf32" else 3e-2
+    assert ((got - xv_ref).abs().max(1).values / xv_ref.norm(dim=1)).max().item() < tol
+    assert ((pooled - pooled_ref).abs().max(1).values / pooled_ref.norm(dim=1)).max().item() < tol
+    cos = torch.nn.functional.cosine_similarity(got, xv_ref, dim=1)
+    assert cos.min().item() > 0.9999
+    assert torch.isfinite(m.forward(x.cuda())).all()

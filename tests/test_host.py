@@ -23,7 +23,9 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib = xvec_b200._lib.load()
-    assert lib.xvec_abi_version() == xvec_b200._lib.ABI_VERSION == 4
+    assert lib.xvec_abi_version() == xvec_b200._lib.ABI_VERSION == int(re.search(r"#define XVEC_ABI_VERSION (\d+)", header).group(1))
+    assert xvec_b200._lib.STACK_MAX_TAP_OFFSET == int(re.search(r"#define XVEC_STACK_MAX_TAP_OFFSET (\d+)", header).group(1))
+    assert lib.xvec_watchdog_code() == 0  # readable without a device: the word lives in host memory
     assert lib.xvec_packed_k(24, 5, xvec_b200._lib.F32) == 160 and lib.xvec_packed_k(512, 3, xvec_b200._lib.BF16) == 1536
     assert lib.xvec_packed_k(3000, 1, xvec_b200._lib.BF16) == 3008 and lib.xvec_packed_n(1500) == 1536
 
@@ -161,6 +163,22 @@ def test_load_reference_checkpoint_roundtrip(tmp_path):
     assert not res.missing_keys and not res.unexpected_keys
     for k, v in sd.items():
         assert torch.equal(m.state_dict()[k], v), k
+
+
+def test_load_reference_checkpoint_rejects_incomplete_and_untrusted(tmp_path):
+    sd = ox.make_state_dict(seed=0)
+    short = {k: v for k, v in sd.items() if not k.startswith("segment_layer6")}
+    path = str(tmp_path / "short.ckpt")
+    torch.save({"state_dict": short}, path)
+    with pytest.raises(KeyError, match="segment_layer6"):     # a silently random-initialised layer would be worse than an error
+        xvec_b200.XVectorModel().load_reference_checkpoint(path)
+
+    class Opaque:                                              # stands for the Lightning objects a real checkpoint may pickle
+        pass
+    path2 = str(tmp_path / "pickled.ckpt")
+    torch.save({"state_dict": sd, "callbacks": Opaque()}, path2)
+    with pytest.raises(RuntimeError, match="trust_pickle"):   # the code-executing unpickler is opt-in only
+        xvec_b200.XVectorModel().load_reference_checkpoint(path2)
 
 
 @pytest.mark.parametrize("rows,band", [(76800, 0), (76800, 5), (76800, 7), (76800, 1000), (300, 0), (257, 3), (131072, 0), (1536000, 0),

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Times the tdnn_stack_kernel launch alone (CUDA events, back-to-back launches) on the bench workload (256 x 300 frames) for a
-sweep of XVEC_BAND / XVEC_STACK_DBG / XVEC_L2HINT settings.  The DBG switches need the debug library:
+sweep of band heights (explicit argument) and XVEC_STACK_DBG / XVEC_L2HINT settings (debug library only).  The DBG switches need the debug library:
     python speaker-recognition-x-vectors_b200/build.py --debug
     XVEC_LIB=$PWD/speaker-recognition-x-vectors_b200/libxvec_b200_debug.so python tools/stack_bench.py --dbg 0,1,2,3,4,7
 """
@@ -37,13 +37,13 @@ part = sc.part[: lay.n_slots]
 flops = args.batch * sum(f * (args.frames - l) for f, l in zip([122880, 1572864, 1572864, 524288, 1536000], [4, 8, 14, 14, 14]))
 
 
-def run(iters):
+def run(iters, band=0):
     evs = []
     for it in range(iters + 3):
         xs = x[it % n_res]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, band=band)
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()
@@ -53,9 +53,8 @@ def run(iters):
 
 for band in args.band.split(","):
     for dbg in args.dbg.split(","):
-        os.environ["XVEC_BAND"] = band
         os.environ["XVEC_STACK_DBG"] = dbg
-        avg, best = run(args.iters)
+        avg, best = run(args.iters, int(band))
         cnt = sc.ctrl[:128].view(torch.int32).tolist()
         extra = ("  counters(spun,polls,fw,pub,mma_full,mma_tempty)=" + str([c for c in cnt[1:7]])) if any(cnt[1:7]) else ""
         if cnt[9]:

@@ -39,13 +39,12 @@ for precision in ("bf16", "tf32"):
         torch.cuda.synchronize()
         streams = [torch.cuda.Stream() for _ in range(2)]
         for band in (0, 5, 9, 33, 0):
-            os.environ["XVEC_BAND"] = str(band)
             parts = [[torch.zeros_like(ref) for _ in range(8)] for _ in range(2)]
             for rep in range(8):
                 for s in range(2):
                     with torch.cuda.stream(streams[s]):
                         ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs if s == 0 else xs1, scs[s].act[0], scs[s].act[1], lay.row_utt,
-                                       lay.blk_slot_base, parts[s][rep], scs[s].ctrl)
+                                       lay.blk_slot_base, parts[s][rep], scs[s].ctrl, band=band)
             torch.cuda.synchronize()
             for s in range(2):
                 for rep in range(8):
