@@ -165,6 +165,10 @@ def test_load_reference_checkpoint_roundtrip(tmp_path):
         assert torch.equal(m.state_dict()[k], v), k
 
 
+class Opaque:  # stands for the Lightning objects (callback state, hyper-parameter containers) a real checkpoint may pickle
+    pass
+
+
 def test_load_reference_checkpoint_rejects_incomplete_and_untrusted(tmp_path):
     sd = ox.make_state_dict(seed=0)
     short = {k: v for k, v in sd.items() if not k.startswith("segment_layer6")}
@@ -173,12 +177,11 @@ def test_load_reference_checkpoint_rejects_incomplete_and_untrusted(tmp_path):
     with pytest.raises(KeyError, match="segment_layer6"):     # a silently random-initialised layer would be worse than an error
         xvec_b200.XVectorModel().load_reference_checkpoint(path)
 
-    class Opaque:                                              # stands for the Lightning objects a real checkpoint may pickle
-        pass
     path2 = str(tmp_path / "pickled.ckpt")
     torch.save({"state_dict": sd, "callbacks": Opaque()}, path2)
     with pytest.raises(RuntimeError, match="trust_pickle"):   # the code-executing unpickler is opt-in only
         xvec_b200.XVectorModel().load_reference_checkpoint(path2)
+    assert not xvec_b200.XVectorModel().load_reference_checkpoint(path2, trust_pickle=True).missing_keys
 
 
 @pytest.mark.parametrize("rows,band", [(76800, 0), (76800, 5), (76800, 7), (76800, 1000), (300, 0), (257, 3), (131072, 0), (1536000, 0),
