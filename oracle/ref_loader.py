@@ -19,7 +19,9 @@ import os
 import sys
 import types
 
-_DEFAULT_DIRS = ("/root/reference",)
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# $XVEC_REF_DIR, the build container's read-only mount, and where a driver-side `pip install --target baseline/_ref` would put it
+_DEFAULT_DIRS = ("/root/reference", os.path.join(_REPO, "baseline", "_ref"))
 
 
 def reference_dir() -> str | None:

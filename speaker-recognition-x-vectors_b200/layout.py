@@ -113,3 +113,32 @@ def bucket_batches(lengths, max_frames: int, max_utts: int = 1 << 30):
     if cur:
         batches.append(np.asarray(cur, dtype=np.int64))
     return batches
+
+
+def balanced_batches(lengths, target_frames: int = 49152, multiple_of: int = 8):
+    """Cut the utterance list (in its given order) into n contiguous batches of nearly equal total frames, n a multiple of
+    `multiple_of` (so that 1, 2, 4 or 8 workers each get the same number of batches).  Returns a list of int64 index arrays.
+
+    This is the unit of sharding that keeps results BIT-identical for any number of GPUs: a batch's composition — and with it
+    the row position of every utterance inside the flat frame matrix, which fixes the fp32 summation order of its pooling — is a
+    function of the lengths alone, never of the world size; worker r simply takes batches r, r + world, ...  (lpt_partition
+    balances single utterances and is exact to one utterance, but a worker's batches then depend on the world size, and the
+    x-vectors agree across world sizes only to fp32 rounding.)  Balance: batches differ by at most one utterance's frames."""
+    lengths = np.asarray(lengths, dtype=np.int64).reshape(-1)
+    if lengths.size == 0:
+        raise ValueError("empty utterance list")
+    total = int(lengths.sum())
+    n = max(1, int(round(total / max(int(target_frames), 1) / multiple_of))) * multiple_of
+    if n > lengths.size:
+        n = int(lengths.size)
+    ends = np.cumsum(lengths)
+    cuts = [0]
+    for k in range(1, n):
+        want = total * k / n
+        j = int(np.searchsorted(ends, want, side="left"))          # utterance boundary nearest to the k-th equal share
+        if j > 0 and abs(int(ends[j - 1]) - want) <= abs(int(ends[min(j, ends.size - 1)]) - want):
+            j -= 1
+        j = min(max(j + 1, cuts[-1] + 1), lengths.size - (n - k))  # at least one utterance per batch, also in the remaining ones
+        cuts.append(j)
+    cuts.append(int(lengths.size))
+    return [np.arange(a, b, dtype=np.int64) for a, b in zip(cuts[:-1], cuts[1:])]

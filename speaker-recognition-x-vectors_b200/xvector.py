@@ -374,9 +374,10 @@ class XVectorModel(nn.Module):
             return self._linear(self.segment_layer7, h6, relu=False, out_dtype=torch.float32)
         return self._linear(self.segment_layer6, a, relu=False, out_dtype=torch.float32)  # 6 and "anything else" (main.py:86-87,91-92)
 
-    def extract_x_vec_flat(self, flat_x: torch.Tensor, lengths, slot: int = 0) -> torch.Tensor:
+    def extract_x_vec_flat(self, flat_x: torch.Tensor, lengths, slot: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
         """Ragged extraction: flat (sum(lengths), input_size) frames -> float32 (len(lengths), x_vector_size).
-        `slot` selects an independent scratch set so that calls on different CUDA streams can overlap.
+        `slot` selects an independent scratch set so that calls on different CUDA streams can overlap; `out` (float32 CUDA,
+        (len(lengths), x_vector_size), unit column stride) receives the x-vectors in place, e.g. a row range of a whole set's matrix.
         The whole path is ONE C-ABI call (xvec_extract_forward) that enqueues its kernels on the current stream: the
         persistent TDNN-stack kernel (all five layers + pooling partials), the pooling finalize and the segment layer(s)."""
         self._check_eval()
@@ -394,7 +395,10 @@ class XVectorModel(nn.Module):
         if flat_x.dtype != torch.float32:
             flat_x = flat_x.float()
         x = self._frames_for(flat_x, pipe)
-        out = torch.empty((lay.n_utts, pipe["out_dim"]), dtype=torch.float32, device=flat_x.device)
+        if out is None:
+            out = torch.empty((lay.n_utts, pipe["out_dim"]), dtype=torch.float32, device=flat_x.device)
+        elif (out.dtype != torch.float32 or out.device != flat_x.device or out.shape != (lay.n_utts, pipe["out_dim"]) or out.stride(1) != 1):
+            raise ValueError(f"out must be a float32 ({lay.n_utts}, {pipe['out_dim']}) tensor on the input's device with unit column stride")
         lib = _lib.load()
         p = _lib.ptr
         with torch.cuda.device(flat_x.device):

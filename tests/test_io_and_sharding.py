@@ -51,8 +51,8 @@ def _free_port():
 
 
 def _fake_extract(utts):
-    # stands in for HostExtractor.extract_all: any per-utterance function of the frames
-    return np.stack([np.concatenate([u.double().mean(0).numpy(), [float(u.shape[0])]]) for u in utts])
+    # stands in for HostExtractor.extract_all: any per-utterance function of the frames (float32-exact values, like x-vectors)
+    return np.stack([np.concatenate([u.double().mean(0).numpy(), [float(u.shape[0])]]) for u in utts]).astype(np.float32).astype(np.float64)
 
 
 def _worker(rank, world, port, lens, q):
@@ -60,15 +60,30 @@ def _worker(rank, world, port, lens, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = torch.Generator().manual_seed(5)
     utts = list(torch.split(torch.randn(int(sum(lens)), 24, generator=g), [int(v) for v in lens]))
-    out = sharding.extract_sharded(utts, _fake_extract)
+    out = sharding.extract_sharded(utts, _fake_extract, dim=25)
     shard = sharding.my_shard(lens, rank, world)
-    q.put((rank, None if out is None else out, shard))
+    # the tensor gather itself: every rank gets every row, in the original order, bit for bit
+    parts = xvec_b200.lpt_partition(lens, world)
+    local = torch.from_numpy(_fake_extract([utts[i] for i in parts[rank]])).float() if len(parts[rank]) else torch.zeros((0, 25))
+    full = sharding.gather_rows(local, parts, len(utts))
+    # batch-granular sharding through a reusable RowGather (two calls: the buffers are reused)
+    bparts, bsizes = sharding.shard_batches(lens, world, target_frames=2000)
+    rg = sharding.RowGather(bparts, len(utts), 25, "cpu")
+    for _ in range(2):
+        if len(bparts[rank]):
+            rg.local_view.copy_(torch.from_numpy(_fake_extract([utts[i] for i in bparts[rank]])).float())
+        full_b = rg().clone()
+    assert torch.equal(full_b, full) and sum(bsizes[rank]) == len(bparts[rank])
+    q.put((rank, None if out is None else out, shard, full.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_extraction_world2_gloo():
-    lens = np.random.default_rng(3).integers(20, 400, 57)
+@pytest.mark.parametrize("n_utts", [57, 1])
+def test_sharded_extraction_world2_gloo(n_utts):
+    """extract_sharded / gather_rows over a real 2-process group (gloo, host tensors): fixed-shape all_gather_into_tensor of
+    padded float32 blocks, no pickled objects; n_utts = 1 leaves rank 1 with an empty shard."""
+    lens = np.random.default_rng(3).integers(20, 400, n_utts)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -77,20 +92,45 @@ def test_sharded_extraction_world2_gloo():
         p.start()
     res = {}
     for _ in procs:
-        r, out, shard = q.get(timeout=120)
-        res[r] = (out, shard)
+        r, out, shard, full = q.get(timeout=120)
+        res[r] = (out, shard, full)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    out0, shard0 = res[0]
-    out1, shard1 = res[1]
-    assert out1 is None and out0.shape == (57, 25)
-    assert np.array_equal(np.sort(np.concatenate([shard0, shard1])), np.arange(57))    # every utterance exactly once
+    out0, shard0, full0 = res[0]
+    out1, shard1, full1 = res[1]
+    assert out1 is None and out0.shape == (n_utts, 25) and out0.dtype == np.float64
+    assert np.array_equal(full0, full1) and np.array_equal(full0.astype(np.float64), out0)     # every rank holds the whole matrix
+    assert np.array_equal(np.sort(np.concatenate([shard0, shard1])), np.arange(n_utts))    # every utterance exactly once
     assert abs(int((lens[shard0] - 14).sum()) - int((lens[shard1] - 14).sum())) <= lens.max()  # balanced
     g = torch.Generator().manual_seed(5)
     utts = list(torch.split(torch.randn(int(lens.sum()), 24, generator=g), [int(v) for v in lens]))
     assert np.array_equal(out0, _fake_extract(utts))                                   # original order restored
     assert np.array_equal(sharding.extract_sharded(utts, _fake_extract), out0)         # world == 1 path
+
+
+def test_balanced_batches_do_not_depend_on_world_size():
+    """shard_batches: contiguous batches of equal frames whose composition is a function of the lengths alone; worker r of any
+    world takes batches r, r + world, ... — the property that makes sharded x-vectors bit-identical for 1, 2, 4, 8 GPUs."""
+    lens = np.random.default_rng(3).integers(400, 2001, 4874)
+    batches = xvec_b200.balanced_batches(lens, target_frames=49152, multiple_of=8)
+    assert len(batches) % 8 == 0 and np.array_equal(np.concatenate(batches), np.arange(4874))
+    frames = np.asarray([lens[b].sum() for b in batches])
+    assert frames.max() - frames.min() <= 2 * lens.max() and abs(frames.mean() - 49152) < 0.05 * 49152
+    for world in (1, 2, 4, 8):
+        parts, sizes = sharding.shard_batches(lens, world)
+        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(4874))
+        loads = np.asarray([lens[p].sum() for p in parts], dtype=np.float64)
+        assert loads.max() / loads.mean() < 1.01
+        for r in range(world):  # rank r's batches are exactly batches r, r + world, ... of the world-independent list
+            assert sizes[r] == [len(b) for b in batches[r::world]]
+            assert np.array_equal(parts[r], np.concatenate(batches[r::world]))
+    for n in (1, 2, 5, 9, 40):  # tiny sets: never an empty batch, every utterance once
+        small = np.random.default_rng(n).integers(20, 400, n)
+        bb = xvec_b200.balanced_batches(small, target_frames=3000)
+        assert all(len(b) for b in bb) and np.array_equal(np.concatenate(bb), np.arange(n))
+        parts, sizes = sharding.shard_batches(small, 4, target_frames=3000)
+        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(n))
 
 
 def test_eer_and_min_dcf_from_first_principles():
