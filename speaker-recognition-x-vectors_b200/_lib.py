@@ -109,9 +109,29 @@ def ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
 
 
-def stream_ptr() -> int:
+def stream_ptr(device_index: int | None = None) -> int:
+    """cudaStream_t of torch's current stream on the given (default: current) device — the raw C query: torch.cuda.current_stream()
+    builds a Python Stream object and costs ~15 us, which matters at ten thousand calls per second and rank."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device() if device_index is None else device_index)
+
+
+class on_device:
+    """`with on_device(dev):` = torch.cuda.device(dev), skipping the device switch (and ~15 us of Python) when `dev` is current."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        import torch
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.ctx = None if idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*a)
 
 
 def dtype_code(torch_dtype) -> int:

@@ -149,6 +149,14 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 __device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// The 128-byte line at `p` (128-byte aligned) holds dead data: L2 may drop it instead of writing it back to HBM.  Semantically a
+// weak write of an indeterminate value — only ever issued on lines whose last reader has finished and whose next access is a write.
+__device__ __forceinline__ void discard_l2_line(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
+__device__ __forceinline__ uint32_t atom_add_relaxed_gpu_u32(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
 // Orders generic-proxy accesses (the flag acquire / release) against async-proxy accesses (TMA loads / stores) of this thread.
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 

@@ -51,6 +51,8 @@ constexpr int SLAB_ROWS_MAX = BM_CTA + XVEC_STACK_MAX_TAP_OFFSET;  // frame rows
 constexpr int SLAB_BYTES = SLAB_ROWS_MAX * BK_BYTES;  // 17 KiB, a multiple of 1024
 static_assert(SLAB_BYTES % 1024 == 0, "slab bases must stay 1024-byte aligned for SWIZZLE_128B");
 constexpr int SCHED_SLOTS = 8;            // work-item ring between the scheduler and the warp roles
+constexpr int CREDIT_BARS = 4;            // "tile started" barriers; the scheduler's run-ahead must stay below this (see the scheduler warp)
+constexpr int STACK_RUNAHEAD = 1;         // items a pair may hold that its producer has not started (p.runahead); measured: 1, 2, 3 give the same launch time
 constexpr uint32_t ITEM_DONE = 0xFFFFFFFFu;
 constexpr int SCHED_CONSUMERS = 2 * EPI_WARPS + 4;  // per slot: both producers, leader MMA warp, peer dependency warp, 8 epilogue warps of each CTA
 constexpr int DEP_WARP = 2 + EPI_WARPS;             // warp 10
@@ -76,11 +78,16 @@ struct StackParams {
   StackLayer L[XVEC_MAX_STACK];
   unsigned* counter;          // next work item (zeroed before the launch)
   unsigned* ready;            // [(n_layers-1)][m_tiles] completed epilogue-warp stores per tile (zeroed before the launch)
+  unsigned* consumed;         // [n_layers][m_tiles] epilogue warps that have seen the tile's MMAs complete (layers >= 1; zeroed)
+  char* act[2];               // the two ping-pong activation buffers (layer l >= 1 reads act[(l-1) & 1]) ...
+  long long act_ld_bytes;     // ... their row pitch; 0 = do not discard consumed activations
+  int act_es;                 // bytes per activation element
   const int* row_utt;
   const int* blk_slot_base;
   float* part;
   unsigned long long pol_a, pol_b, pol_y;
   int dbg;
+  int runahead;               // scheduler run-ahead depth, 1 .. CREDIT_BARS - 1
   unsigned band_first[XVEC_STACK_MAX_BANDS + 1];
 };
 
@@ -109,7 +116,8 @@ __host__ __device__ inline uint32_t decode_item(const StackParams& p, unsigned i
 // signalling (only together with 1 — alone it makes the dependency warps spin until the watchdog fires, which is what
 // tests/test_gpu_kernels.py::test_watchdog_code_is_readable uses), 4 skip the proxy fences (results are then undefined; timing
 // experiments only), 8 short watchdog limit for the dependency spin (2^12 polls instead of 2^24), 16 the dependency watchdog
-// reports its code and stops waiting instead of trapping (a trap is an Xid event on the box; the test only needs the code).
+// reports its code and stops waiting instead of trapping (a trap is an Xid event on the box; the test only needs the code),
+// 32 / 64 timing experiments: no activation loads for n-tiles > 0 of single-tap layers / no epilogue work at all.
 // Debug builds also accumulate counters in the spare words of the control block (read by tools/stack_bench.py; units of 64
 // cycles unless stated): 1 tiles whose dependency warp had to spin on a flag (count), 2 flag polls (count), 3 producer waiting
 // for its dependency warp, 4 producer waiting for the work item, 5 MMA warp waiting for operands (explicit waits only),
@@ -131,19 +139,20 @@ struct MmaRing {
 };
 template <bool kTf32>
 __device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* fa, uint64_t* ea, uint64_t* fb, uint64_t* eb, uint32_t d, const StackLayer& L,
-                                         MmaRing& r, bool swap_ab, unsigned long long& c_wait, unsigned long long& c_step) {
+                                         MmaRing& r, bool swap_ab, unsigned long long& c_wait, unsigned long long& c_step, bool no_a = false) {
   constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
   uint32_t acc = 0;
   for (int ch = 0; ch < L.cpt; ++ch) {
-    if (!(r.rdy & 1u)) {
+    if (!(r.rdy & 1u) && !no_a) {
       XVEC_CNT(const long long t0 = clock64();)
       mbar_wait(&fa[r.slab], r.aph, 3);
       XVEC_CNT(c_wait += clock64() - t0;)
     }
-    r.rdy &= ~1u;  // bit0 is set again by the last tap's probe of the NEXT slab
+    if (!no_a) r.rdy &= ~1u;  // bit0 is set again by the last tap's probe of the NEXT slab
     int slab_n = r.slab + 1;
     uint32_t aph_n = r.aph;
     if (slab_n == A_SLABS) { slab_n = 0; aph_n ^= 1u; }
+    if (no_a) { slab_n = r.slab; aph_n = r.aph; }  // timing experiment (debug bit 128): no slab hand-over at all
     const uint32_t slab_addr = smem_u32(base + r.slab * SLAB_BYTES);
     for (int tap = 0; tap < L.taps; ++tap) {
       if (!(r.rdy & 2u)) {
@@ -162,12 +171,12 @@ __device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* fa, uint64_t* 
       uint32_t bph_n = r.bph;
       if (bst_n == B_STAGES) { bst_n = 0; bph_n ^= 1u; }
       const bool last_tap = tap == L.taps - 1;
-      const uint32_t flags = STEP_COMMIT_B | STEP_PROBE_B | (last_tap ? (STEP_COMMIT_A | STEP_PROBE_A) : 0u);
+      const uint32_t flags = STEP_COMMIT_B | STEP_PROBE_B | ((last_tap && !no_a) ? (STEP_COMMIT_A | STEP_PROBE_A) : 0u);
       XVEC_CNT(const long long ts = clock64();)
       const uint32_t got = umma_step_pair<kTf32>(elect_one() ? 1u : 0u, d, da, db, idesc, acc, flags, smem_u32(&ea[r.slab]),
                                                  smem_u32(&eb[r.bst]), smem_u32(&fa[slab_n]), aph_n, smem_u32(&fb[bst_n]), bph_n);
       XVEC_CNT(c_step += clock64() - ts;)
-      r.rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
+      r.rdy = (got & 2u) | ((last_tap && !no_a) ? (got & 1u) : (no_a ? (r.rdy & 1u) : 0u));
       acc = 1u;
       r.bst = bst_n;
       r.bph = bph_n;
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1)
 tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant__ StackParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t fa_bar[A_SLABS], ea_bar[A_SLABS], fb_bar[B_STAGES], eb_bar[B_STAGES], tfull_bar[2], tempty_bar[2];
-  __shared__ uint64_t sfull_bar[SCHED_SLOTS], sempty_bar[SCHED_SLOTS], dep_bar[SCHED_SLOTS], credit_bar;
+  __shared__ uint64_t sfull_bar[SCHED_SLOTS], sempty_bar[SCHED_SLOTS], dep_bar[SCHED_SLOTS], credit_bar[CREDIT_BARS];
   __shared__ uint32_t sched_item[SCHED_SLOTS];
   __shared__ uint32_t tmem_base_smem;
 
@@ -218,7 +227,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       mbar_init(&sempty_bar[s], SCHED_CONSUMERS);  // every consumer of both CTAs, on the leader's barrier
       mbar_init(&dep_bar[s], 1);                   // this CTA's dependency warp
     }
-    mbar_init(&credit_bar, 1);  // leader's producer, once per tile
+    for (int c = 0; c < CREDIT_BARS; ++c) mbar_init(&credit_bar[c], 1);  // leader's producer: tile j arrives on credit_bar[j % CREDIT_BARS]
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_pair<TMEM_COLS>(&tmem_base_smem);
@@ -255,7 +264,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       if (item == ITEM_DONE) break;
       mbar_wait(&dep_bar[it % SCHED_SLOTS], (it / SCHED_SLOTS) & 1u, 7);
       XVEC_CNT(c_fw += clock64() - t0;)
-      if (rank == 0 && lane == 0) mbar_arrive(&credit_bar);  // tile `it` has started: the scheduler may draw item it+1
+      if (rank == 0 && lane == 0) mbar_arrive(&credit_bar[it % CREDIT_BARS]);  // tile `it` has started: the scheduler may draw item it + run-ahead
       const int layer = item & 7u, nt = (item >> 3) & 31u, mt = item >> 8;
       const StackLayer& L = p.L[layer];
       const int bke = (kAllTf32 || L.tf32) ? 32 : 64;  // elements per 128-byte chunk
@@ -264,25 +273,31 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       const CUtensorMap* ma = &maps.a[layer];
       const CUtensorMap* mb = &maps.b[layer];
       const uint32_t slab_tx = 2u * static_cast<uint32_t>(L.slab_rows) * BK_BYTES;  // bytes of both CTAs' slabs
+      // timing experiment (debug bit 32): no activation loads for n-tiles > 0 of single-tap layers, as if the m-tile's activation
+      // chunks were resident in shared memory (the MMAs then read stale slabs: wrong results, right timing)
+      const bool skip_a = XVEC_SDBG(p, 32 | 128) && L.taps == 1 && nt > 0;
+      const bool no_a = XVEC_SDBG(p, 128) && L.taps == 1 && nt > 0;  // (bit 128) ... and no slab barrier hand-over either
       for (int ch = 0; ch < L.cpt; ++ch) {
-        if (!(rdy & 1u)) mbar_wait(&ea_bar[slab], aph ^ 1u, 1);
+        if (!(rdy & 1u) && !no_a) mbar_wait(&ea_bar[slab], aph ^ 1u, 1);
         int slab_n = slab + 1;
         uint32_t aph_n = aph;
         if (slab_n == A_SLABS) { slab_n = 0; aph_n ^= 1u; }
-        rdy &= ~1u;
+        if (no_a) { slab_n = slab; aph_n = aph; }
+        else rdy &= ~1u;
         for (int tap = 0; tap < L.taps; ++tap) {
           if (!(rdy & 2u)) mbar_wait(&eb_bar[bst], bph ^ 1u, 1);
           int bst_n = bst + 1;
           uint32_t bph_n = bph;
           if (bst_n == B_STAGES) { bst_n = 0; bph_n ^= 1u; }
           const bool last_tap = tap == L.taps - 1;
+          if (skip_a && !no_a && tap == 0 && rank == 0 && elect_one()) mbar_expect_tx(&fa_bar[slab], 0);  // completes the phase with no bytes
           const uint32_t got = tma_step_slab(
-              elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, tap == 0 ? 1u : 0u, smem_u32(&fa_bar[slab]), mapa_u32(smem_u32(&fa_bar[slab]), 0),
+              elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, (tap == 0 && !skip_a) ? 1u : 0u, smem_u32(&fa_bar[slab]), mapa_u32(smem_u32(&fa_bar[slab]), 0),
               slab_tx, smem_u32(base + slab * SLAB_BYTES), ma, ch * bke, m0, p.pol_a, smem_u32(&fb_bar[bst]),
               mapa_u32(smem_u32(&fb_bar[bst]), 0), 2u * B_BYTES, smem_u32(base + A_SLABS * SLAB_BYTES + bst * B_BYTES), mb,
-              0, (tap * L.cpt + ch) * L.n_pad + n0, p.pol_b, smem_u32(&eb_bar[bst_n]), bph_n ^ 1u, last_tap ? 1u : 0u, smem_u32(&ea_bar[slab_n]),
+              0, (tap * L.cpt + ch) * L.n_pad + n0, p.pol_b, smem_u32(&eb_bar[bst_n]), bph_n ^ 1u, (last_tap && !no_a) ? 1u : 0u, smem_u32(&ea_bar[slab_n]),
               aph_n ^ 1u);
-          rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
+          rdy = (got & 2u) | ((last_tap && !no_a) ? (got & 1u) : (no_a ? (rdy & 1u) : 0u));
           bst = bst_n;
           bph = bph_n;
         }
@@ -312,8 +327,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         XVEC_CNT(c_tempty += clock64() - t0; const int dl = item & 7u; if (lane == 0) atomicAdd(p.counter + 16 + dl, static_cast<unsigned>((clock64() - t0) >> 4));)
         const uint32_t d = tmem_base + buf * BN;
         const bool pooled = static_cast<int>(item & 7u) == p.n_layers - 1;  // last layer: transposed accumulator (see the epilogue)
-        if (kAllTf32 || L.tf32) mma_tile<true>(base, fa_bar, ea_bar, fb_bar, eb_bar, d, L, ring, pooled, c_full, c_step);
-        else mma_tile<false>(base, fa_bar, ea_bar, fb_bar, eb_bar, d, L, ring, pooled, c_full, c_step);
+        const bool no_a = XVEC_SDBG(p, 128) && L.taps == 1 && ((item >> 3) & 31u) > 0;
+        if (kAllTf32 || L.tf32) mma_tile<true>(base, fa_bar, ea_bar, fb_bar, eb_bar, d, L, ring, pooled, c_full, c_step, no_a);
+        else mma_tile<false>(base, fa_bar, ea_bar, fb_bar, eb_bar, d, L, ring, pooled, c_full, c_step, no_a);
         if (elect_one()) umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
         __syncwarp();
         XVEC_CNT(if (lane == 0) atomicAdd(p.counter + 24 + (item & 7u), static_cast<unsigned>((clock64() - tr) >> 4));)
@@ -328,23 +344,32 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   } else if (warp == DEP_WARP) {
     // ------------------------------------------------------------------ scheduler (leader) + dependency warp (both CTAs)
     // Leader: draws work items (atomicAdd on the global counter), decodes them and publishes them in the ring of both CTAs —
-    // item it+1 as soon as the producer has started tile `it` (credit_bar), so a pair never holds more than one item it has
-    // not begun (a deeper run-ahead would only lengthen the tail of the launch).
+    // item `it` as soon as the producer has started tile it - D (credit_bar), D = p.runahead (1: a pair never holds more than one
+    // item it has not begun).  Measured on B200 (256 x 300, bf16): D = 1, 2, 3 give the same tile times and the same launch time
+    // (297.7 / 298.3 / 299.6 us) — the chain "tile started -> atomic -> decode -> publication -> dependency acquire" is not what
+    // the K = 512 tiles of TDNN4/5 wait for.  Near the end of the queue (fewer than (D + 1) x pairs items left) the depth falls
+    // back to 1, so that no pair sits on unstarted items while others have run out of work.
     // Both CTAs: resolve the inter-layer dependencies of every item ahead of the producer: lanes 0..2 poll (ld.acquire.gpu)
     // the flags of the tiles the item touches — reads: this CTA's 128 rows + the taps' reach (rank 1 runs into tile mt+1);
     // writes: rows whose old contents (two layers back, same ping-pong buffer) tiles mt-1 and mt of the previous layer were
     // reading — then fence.proxy.async (flag in the generic proxy -> tile data in the async proxy), one arrive on dep_bar.
     XVEC_CNT(unsigned long long c_spun = 0, c_polls = 0;)
     int band_cursor = 0;
+    unsigned raw_prev = 0;  // the last item this pair drew
     for (int it = 0;; ++it) {
       uint32_t item;
       if (rank == 0) {
         const int slot = it % SCHED_SLOTS;
         const uint32_t sph = (it / SCHED_SLOTS) & 1u;
-        if (it > 0) mbar_wait(&credit_bar, (it - 1) & 1u, 8);
+        {
+          const int depth = (raw_prev + static_cast<unsigned>(p.runahead + 1) * (gridDim.x >> 1) >= p.total_items) ? 1 : p.runahead;
+          const int j = it - depth;  // the tile whose start is awaited; tile j arrives in phase j / CREDIT_BARS of credit_bar[j % CREDIT_BARS]
+          if (j >= 0) mbar_wait(&credit_bar[j % CREDIT_BARS], static_cast<uint32_t>(j / CREDIT_BARS) & 1u, 8);
+        }
         unsigned raw = 0;
         if (lane == 0) raw = atomicAdd(p.counter, 1u);
         raw = __shfl_sync(0xffffffffu, raw, 0);
+        raw_prev = raw;
         item = raw < p.total_items ? decode_item(p, raw, band_cursor) : ITEM_DONE;
         mbar_wait(&sempty_bar[slot], sph ^ 1u, 5);
         if (lane == 0) {
@@ -425,6 +450,31 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       if (pend && !mbar_test_wait(&tfull_bar[buf], use)) flush();
       mbar_wait(&tfull_bar[buf], use, 4);
       tc_fence_after();
+#ifdef XVEC_DEBUG
+      if (layer > 0 && p.act_ld_bytes) {
+        // EXPERIMENT (debug builds, XVEC_STACK_DISCARD=1; measured on B200: DRAM writes per launch 187 MB -> 17.5 MB, but CCTL.RML2
+        // retires one 128-byte line per ~75 cycles and SM, so the 2.4 M lines of a 256 x 300 batch make the launch 3x slower:
+        // 296 -> 934 us.  Kept as the record of that measurement, not compiled into the product library.)
+        // Dead activations: every MMA of this item is complete, so its share of the reads of layer-1's rows is over.  The warp
+        // that sees the LAST of the (n_tiles x 2 CTAs x EPI_WARPS) arrivals for (layer, mt) tells L2 to drop rows
+        // [256 mt + 8, 256 mt + 256) of the input buffer instead of writing them back to HBM: the first 8 rows are also read by
+        // tile mt-1 (tap offsets <= 8), everything else has no reader left, and the next access is the write of tile
+        // (layer+1, mt), which waits for ready[layer][mt] — published by this very warp only after the discards below.
+        unsigned old = 0;
+        if (lane == 0) old = atom_add_relaxed_gpu_u32(p.consumed + static_cast<size_t>(layer) * p.m_tiles + mt, 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old + 1 == static_cast<unsigned>(L.n_tiles) * 2u * EPI_WARPS) {
+          const int r_lo = mt * BM + XVEC_STACK_MAX_TAP_OFFSET;
+          const int r_hi = min(mt * BM + BM, p.rows);
+          const int lines = (p.L[layer - 1].n * p.act_es) >> 7;  // 128-byte lines per row (stored layers are whole 256-channel tiles)
+          char* in = p.act[(layer - 1) & 1];
+          for (int r = r_lo; r < r_hi; ++r) {
+            char* row = in + static_cast<long long>(r) * p.act_ld_bytes;
+            for (int i = lane; i < lines; i += 32) discard_l2_line(row + (i << 7));
+          }
+        }
+      }
+#endif
       const uint32_t tbase = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
       const int row0 = m0 + q * 32;
       bool released = false;
@@ -435,6 +485,12 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         released = true;
       };
 
+      if (XVEC_SDBG(p, 64)) {  // timing experiment: no epilogue at all (no tcgen05.ld, no math, no stores); completion is still published
+        release_tmem();
+        if (pend) flush();
+        if (layer != p.n_layers - 1) pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
+        continue;
+      }
       if (layer == p.n_layers - 1) {
         // Last layer: statistics-pooling partials; nothing is stored and nobody waits for this tile.  The accumulator is
         // TRANSPOSED (the MMA warp swapped the operands): TMEM lane = output channel, column = frame (gemm_tile.cuh).
@@ -594,7 +650,7 @@ int64_t stack_plan(int64_t rows, int n_layers, const int32_t* n_tiles_per_layer,
 int64_t stack_ctrl_bytes(int64_t rows, int n_layers) {
   if (rows <= 0 || n_layers < 2) return 0;
   const int64_t m_tiles = (rows + BM - 1) / BM;
-  return 128 + (n_layers - 1) * m_tiles * 4;
+  return 128 + (n_layers - 1) * m_tiles * 4 + n_layers * m_tiles * 4;  // counters | ready[layers - 1][m_tiles] | consumed[layers][m_tiles]
 }
 
 XVEC_DEFINE_WATCHDOG_BINDER(bind_watchdog_stack)
@@ -734,6 +790,13 @@ static int build_plan(StackPlan& pl, const XvecLayerDesc* tdnn, int n_tdnn, cons
   rc = fill_schedule(p, pick_band(p.m_tiles, n_tdnn, max_pairs, band));
   if (rc) return rc;
   l2_policies(&p.pol_a, &p.pol_b, &p.pol_y);
+  p.runahead = STACK_RUNAHEAD;
+#ifdef XVEC_DEBUG
+  if (const char* e = getenv("XVEC_STACK_RUNAHEAD")) {
+    const int v = atoi(e);
+    if (v >= 1 && v < CREDIT_BARS) p.runahead = v;
+  }
+#endif
   int64_t pairs = static_cast<int64_t>(p.total_items) < max_pairs ? p.total_items : max_pairs;
 #ifdef XVEC_DEBUG
   if (const char* e = getenv("XVEC_STACK_PAIRS")) {  // experiment: fewer CTA pairs (is the operand stream a per-SM or a global limit?)
@@ -805,6 +868,11 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
   }
   p.counter = static_cast<unsigned*>(ctrl);
   p.ready = reinterpret_cast<unsigned*>(static_cast<char*>(ctrl) + 128);
+  p.consumed = p.ready + static_cast<size_t>(n_tdnn - 1) * p.m_tiles;
+  p.act[0] = static_cast<char*>(act0);
+  p.act[1] = static_cast<char*>(act1);
+  p.act_es = tdnn[1].dtype == XVEC_BF16 ? 2 : 4;
+  p.act_ld_bytes = 0;
   p.row_utt = row_utt;
   p.blk_slot_base = blk_slot_base;
   p.part = part;
@@ -812,6 +880,11 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
   {
     const char* e = getenv("XVEC_STACK_DBG");
     p.dbg = e ? atoi(e) : 0;
+    if (getenv("XVEC_STACK_DISCARD")) {  // experiment: drop consumed activation rows from L2 (discard.global.L2) instead of writing them back
+      const long long ldb = act_ld * p.act_es;
+      const bool aligned = ((reinterpret_cast<uintptr_t>(act0) | reinterpret_cast<uintptr_t>(act1)) & 127u) == 0 && ldb % 128 == 0;
+      p.act_ld_bytes = aligned ? ldb : 0;
+    }
   }
 #endif
   cudaStream_t st = static_cast<cudaStream_t>(stream);

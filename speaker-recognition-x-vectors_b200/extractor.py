@@ -14,6 +14,8 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
+from . import _lib
+
 
 
 @dataclass
@@ -71,7 +73,7 @@ class HostExtractor:
         rows, c = x_host.shape
         n_utts = len(lengths)
         dim = (self.model.segment_layer7 if self.model.x_vec_extract_layer == 7 else self.model.segment_layer6).out_features
-        with torch.cuda.device(self.device), torch.cuda.stream(sl.stream):
+        with _lib.on_device(self.device), torch.cuda.stream(sl.stream):
             if sl.x_dev is None or sl.x_dev.shape[0] < rows or sl.x_dev.shape[1] != c:
                 sl.x_dev = torch.empty((rows, c), dtype=torch.float32, device=self.device)
             if out_dev is None and (sl.out_host is None or sl.out_host.shape[0] < n_utts or sl.out_host.shape[1] != dim):

@@ -50,7 +50,7 @@ def pack_weight(weight: torch.Tensor, taps: int, cin: int, dtype: torch.dtype) -
         raise ValueError(f"weight has {w.shape[1]} columns, expected taps*cin = {taps * cin}")
     code = dtype_code(dtype)
     out = torch.empty((lib.xvec_packed_n(n), lib.xvec_packed_k(cin, taps, code)), dtype=dtype, device=w.device)
-    with torch.cuda.device(w.device):
+    with _lib.on_device(w.device):
         check(lib.xvec_pack_weight(ptr(w), n, taps, cin, code, ptr(out), stream_ptr()))
     return out
 
@@ -76,7 +76,7 @@ def tdnn_layer_flat(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
                                 for v in (bias, bn_scale, bn_shift)]
     offs = taps_array(offsets)
     ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         check(lib.xvec_tdnn_layer(ptr(x), dtype_code(x.dtype), rows, cin, x_ld, ptr(w_packed), n, offs, len(offsets),
                                   ptr(bias), ptr(bn_scale), ptr(bn_shift), int(bool(relu)), ptr(out), dtype_code(out.dtype),
                                   y_ld, rows, ptr(workspace), ws_bytes, stream_ptr()))
@@ -101,7 +101,7 @@ def tdnn_pool_fused(x: torch.Tensor, w_packed: torch.Tensor, n: int, offsets, bi
     if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * (256 // _lib.POOL_BLOCK) or not part.is_contiguous():
         raise ValueError("pooling bookkeeping arrays are too small for this frame matrix")
     offs = taps_array(offsets)
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         check(lib.xvec_tdnn_pool_fused(ptr(x), dtype_code(x.dtype), rows, x.shape[1], x_ld, ptr(w_packed), n, offs, len(offsets),
                                        ptr(bias), ptr(row_utt), ptr(blk_slot_base), ptr(part), rows, stream_ptr()))
     return part
@@ -123,7 +123,7 @@ def tdnn_stack(layer_descs, n_layers: int, x: torch.Tensor, act0: torch.Tensor, 
         raise ValueError("activation buffers are too small for this frame matrix")
     if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * (256 // _lib.POOL_BLOCK) or not part.is_contiguous():
         raise ValueError("pooling bookkeeping arrays are too small for this frame matrix")
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         check(lib.xvec_tdnn_stack(layer_descs, n_layers, ptr(x), rows, x_ld, ptr(act0), ptr(act1), act_ld, ptr(row_utt), ptr(blk_slot_base),
                                   ptr(part), ptr(ctrl), ctrl.numel(), int(band), stream_ptr()))
     return part
@@ -146,7 +146,7 @@ def pool_finalize(part: torch.Tensor, slot_start: torch.Tensor, n_rows: torch.Te
     if out_lp is not None:
         lp_ld = _rowmajor_2d(out_lp, "out_lp")
         lp_code = dtype_code(out_lp.dtype)
-    with torch.cuda.device(part.device):
+    with _lib.on_device(part.device):
         check(lib.xvec_pool_finalize(ptr(part), ptr(slot_start), ptr(n_rows), n_utts, p, ptr(bn_scale), ptr(bn_shift), ptr(pivot), ptr(out),
                                      ptr(out_lp), lp_code, lp_ld, stream_ptr()))
     return out
@@ -161,7 +161,7 @@ def build_layout_device(starts: torch.Tensor, n_pool: torch.Tensor, slot_start: 
         raise ValueError("layout arrays must be contiguous int32")
     if row_utt.numel() < rows or blk_slot_base.numel() < ((rows + 255) // 256) * (256 // _lib.POOL_BLOCK) or slot_start.numel() < starts.numel() + 1:
         raise ValueError("layout output arrays are too small")
-    with torch.cuda.device(starts.device):
+    with _lib.on_device(starts.device):
         check(lib.xvec_build_layout(ptr(starts), ptr(n_pool), ptr(slot_start), starts.numel(), rows, ptr(row_utt), ptr(blk_slot_base),
                                     stream_ptr()))
 
@@ -192,7 +192,7 @@ def stats_pool_ragged(x: torch.Tensor, row_start: np.ndarray, n_rows: np.ndarray
     rs_d, nr_d, ss_d, n_slots, max_chunks = hit
     part = torch.empty((n_slots, 2, p), dtype=torch.float32, device=dev)
     pivot = torch.empty((len(n_rows), p), dtype=torch.float32, device=dev)  # each utterance's first row: the sums are shifted by it
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         check(lib.xvec_stats_pool_partial(ptr(x), dtype_code(x.dtype), ld, p, ptr(rs_d), ptr(nr_d), ptr(ss_d), len(n_rows),
                                           max_chunks, ptr(part), ptr(pivot), stream_ptr()))
     return pool_finalize(part, ss_d, nr_d, p, out_lp=out_lp, pivot=pivot)
@@ -224,7 +224,7 @@ def mfcc(wav: torch.Tensor, wav_lengths, normalize: bool = True, out: torch.Tens
     if out.dim() != 2 or out.shape[0] != total or out.shape[1] < 24 or out.stride(1) != 1 or out.dtype != torch.float32:
         raise ValueError("out must be float32 (sum frames, >=24) with unit column stride")
     is16 = int(wav.dtype == torch.int16)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         off = scl = None
         if normalize:
             off = torch.empty(wl.size, dtype=torch.float32, device=dev)
@@ -244,7 +244,7 @@ def cast(src: torch.Tensor, dtype: torch.dtype, out: torch.Tensor | None = None)
     if out is None:
         out = torch.empty(src.shape, dtype=dtype, device=src.device)
     d_ld = _rowmajor_2d(out, "out")
-    with torch.cuda.device(src.device):
+    with _lib.on_device(src.device):
         check(lib.xvec_cast(ptr(src), s_ld, ptr(out), dtype_code(out.dtype), d_ld, src.shape[0], src.shape[1], stream_ptr()))
     return out
 
@@ -264,7 +264,7 @@ def cosine_trials(xvecs: torch.Tensor, enrol: torch.Tensor, test: torch.Tensor, 
     mean = None
     if center:
         mean = stats_pool_ragged(xvecs, np.zeros(1, np.int64), np.asarray([xvecs.shape[0]], np.int32))[0, : xvecs.shape[1]].contiguous()
-    with torch.cuda.device(xvecs.device):
+    with _lib.on_device(xvecs.device):
         check(lib.xvec_cosine_trials(ptr(xvecs), ld, xvecs.shape[1], ptr(mean), ptr(enrol.contiguous()), ptr(test.contiguous()), n,
                                      ptr(out), stream_ptr()))
     return out
@@ -285,13 +285,13 @@ def plda_trials(xvecs: torch.Tensor, mean: torch.Tensor, w_phi: torch.Tensor, b_
         raise ValueError("enrol and test must have the same length")
     x = xvecs
     x3 = torch.empty((n, 3 * d), dtype=torch.float32, device=x.device)  # [hi | lo | hi]: split-TF32 operand of both GEMMs
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         check(lib.xvec_split_tf32(ptr(x), ld, n, d, ptr(x3), x3.stride(0), stream_ptr()))
     y = tdnn_layer_flat(x3, w_phi, d, [0], b_phi, None, None, relu=False, out_dtype=torch.float32, cin=3 * d)  # (x - mean) Phi
     p = tdnn_layer_flat(x3, w_psi, d, [0], b_psi, None, None, relu=False, out_dtype=torch.float32, cin=3 * d)  # (x - mean) Psi
     q = torch.empty(n, dtype=torch.float32, device=x.device)
     out = torch.empty(enrol.numel(), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         check(lib.xvec_plda_rowterm(ptr(x), x.stride(0), d, ptr(mean), ptr(y), y.stride(0), n, ptr(q), stream_ptr()))
         check(lib.xvec_plda_trials(ptr(x), x.stride(0), d, ptr(mean), ptr(p), p.stride(0), ptr(q), ptr(enrol.contiguous()),
                                    ptr(test.contiguous()), enrol.numel(), float(cst), float(scale), ptr(out), stream_ptr()))
@@ -311,7 +311,7 @@ def linear_small(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | Non
         raise ValueError("x and weight disagree on k")
     out = torch.empty((x.shape[0], weight.shape[0]), dtype=out_dtype, device=x.device)
     b = None if bias is None else bias.detach().float().contiguous()
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         check(lib.xvec_linear_small(ptr(x), dtype_code(x.dtype), x.shape[0], x.shape[1], x_ld, ptr(weight), weight.shape[0], w_ld, ptr(b),
                                     int(bool(relu)), ptr(out), dtype_code(out_dtype), out.stride(0), stream_ptr()))
     return out

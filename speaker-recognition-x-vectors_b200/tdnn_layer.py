@@ -44,12 +44,25 @@ class TdnnLayer(nn.Module):
 
     # ------------------------------------------------------------------ parameter preparation (cached)
     def _fingerprint(self):
-        ts = [self.linear.weight, self.linear.bias]
+        """(identity, in-place version) per parameter / buffer: .to()/.cuda() create new tensors (new identity), load_state_dict
+        and optimiser steps bump the version, replacing a sub-module changes the dicts.  Read straight from the modules'
+        parameter dicts — this runs once per batch and layer, and nn.Module.__getattr__ costs more than the comparison."""
+        mods = self._modules
+        lin = mods["linear"]
+        out = [id(lin)]
+        for t in lin._parameters.values():
+            if t is not None:
+                out.append(id(t))
+                out.append(t._version)
         if self.batch_norm:
-            ts += [self.norm.weight, self.norm.bias, self.norm.running_mean, self.norm.running_var]
-        # (identity, in-place version) per parameter: cheap enough for the per-batch hot path; .to()/.cuda() create new
-        # tensors (new identity), load_state_dict / optimiser steps bump the version
-        return tuple((id(t), t._version) for t in ts if t is not None)
+            norm = mods["norm"]
+            out.append(id(norm))
+            for d in (norm._parameters, norm._buffers):
+                for t in d.values():
+                    if t is not None:
+                        out.append(id(t))
+                        out.append(t._version)
+        return tuple(out)
 
     def prepared(self, dtype: torch.dtype, fold_bn: bool = True):
         """(w_packed, bias, bn_scale, bn_shift) on the parameters' device; re-packed when parameters change."""

@@ -170,7 +170,7 @@ class XVectorModel(nn.Module):
         return sum(tap_offsets(l.context)[-1] for l in self.time_context_layers)
 
     def _device(self):
-        return self.segment_layer6.weight.device
+        return self._modules["segment_layer6"]._parameters["weight"].device
 
     def _check_eval(self):
         if self.training:
@@ -179,10 +179,10 @@ class XVectorModel(nn.Module):
     def _layout_for(self, lengths) -> _Layout:
         lengths = np.asarray(lengths, dtype=np.int64)
         dev = self._device()
-        key = (lengths.tobytes(), str(dev), torch.cuda.current_stream().cuda_stream)
+        key = (lengths.tobytes(), dev.index, _lib.stream_ptr(dev.index))
         lay = self._layouts.get(key)
         if lay is None:
-            st = self._scratch.setdefault(("pin", key[1]), _PinnedStaging())  # one ring per device: its buffers are event-guarded
+            st = self._scratch.setdefault(("pin", str(dev)), _PinnedStaging())  # one ring per device: its buffers are event-guarded
             lay = _Layout(lengths, self.lost_frames, dev, st)
             self._layouts[key] = lay
             while len(self._layouts) > 128:
@@ -193,7 +193,7 @@ class XVectorModel(nn.Module):
 
     def _scratch_for(self, slot: int) -> _Scratch:
         dev = self._device()
-        key = (str(dev), self.precision, slot)
+        key = (dev.index, self.precision, slot)
         sc = self._scratch.get(key)
         if sc is None:
             layers = list(self.time_context_layers)
@@ -245,11 +245,12 @@ class XVectorModel(nn.Module):
 
     def _pipeline(self):
         """XvecLayerDesc arrays for xvec_extract_forward (one C call per batch), rebuilt when parameters change."""
-        layers = list(self.time_context_layers)
+        mods = self._modules
+        layers = list(mods["time_context_layers"]._modules.values())
         use7 = self.x_vec_extract_layer == 7
-        fcs = [self.segment_layer6, self.segment_layer7] if use7 else [self.segment_layer6]
+        fcs = [mods["segment_layer6"], mods["segment_layer7"]] if use7 else [mods["segment_layer6"]]
         fp = (tuple(l._fingerprint() for l in layers), self.precision, use7,
-              tuple((id(f.weight), f.weight._version, id(f.bias), f.bias._version if f.bias is not None else -1) for f in fcs))
+              tuple((id(t), t._version) for f in fcs for t in f._parameters.values() if t is not None))
         hit = self._fc_prep.get("pipeline")
         if hit is not None and hit[0] == fp:
             return hit[1]
@@ -312,7 +313,7 @@ class XVectorModel(nn.Module):
 
     def _linear(self, lin: nn.Linear, x2d: torch.Tensor, relu: bool, out_dtype) -> torch.Tensor:
         w, b = self._fc(lin, x2d.dtype)
-        key = ("ws", x2d.shape[0], lin.in_features, lin.out_features, x2d.dtype, str(x2d.device), torch.cuda.current_stream().cuda_stream)
+        key = ("ws", x2d.shape[0], lin.in_features, lin.out_features, x2d.dtype, str(x2d.device), _lib.stream_ptr(x2d.device.index))
         if key not in self._fc_prep:
             self._fc_prep[key] = ops.splitk_workspace(x2d.shape[0], lin.in_features, 1, lin.out_features, x2d.dtype, x2d.device)
         return ops.tdnn_layer_flat(x2d, w, lin.out_features, [0], b, None, None, relu=relu, out_dtype=out_dtype, cin=lin.in_features,
@@ -401,7 +402,7 @@ class XVectorModel(nn.Module):
             raise ValueError(f"out must be a float32 ({lay.n_utts}, {pipe['out_dim']}) tensor on the input's device with unit column stride")
         lib = _lib.load()
         p = _lib.ptr
-        with torch.cuda.device(flat_x.device):
+        with _lib.on_device(flat_x.device):
             _lib.check(lib.xvec_extract_forward(
                 pipe["tdnn"], pipe["n_tdnn"], p(x), lay.rows, x.stride(0), p(sc.act[0]), p(sc.act[1]), sc.ld, p(lay.row_utt),
                 p(lay.blk_slot_base), p(lay.utt_slot_start), p(lay.n_pool), lay.n_utts, p(sc.part), p(pipe["scale5"]), p(pipe["shift5"]),
