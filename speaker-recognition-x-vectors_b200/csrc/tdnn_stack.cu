@@ -35,21 +35,36 @@ namespace xvec {
 // rows and reused by every tap of the layer — tap j's MMA reads the slab through a descriptor whose start address is shifted
 // by tap_off[j] rows (the 128-byte swizzle is a function of the absolute shared-memory address, so a row shift keeps TMA's
 // and UMMA's patterns in step as long as the slab base is 1024-byte aligned).  The weight ("B") side streams one 128 x 128-byte
-// tile per (chunk, tap).  The kernel is bound by the L2 -> SM operand traffic (measured: the MMA warp waits ~350 of every ~650
-// cycles per K chunk for operands), and slabs cut it from 32 KiB to 16 + 17/taps KiB per K chunk.
-// Ring depths, measured on B200 (256 x 300 frames, bf16; slabs / weight stages / store staging boxes per epilogue warp):
-// 4/5/2 316 us, 5/4/2 333 us, 6/5/1 308 us, 5/6/1 302 us — operand bytes in flight matter more than a second staging box.
-#ifndef XVEC_A_SLABS
-#define XVEC_A_SLABS 5
-#define XVEC_B_STAGES 6
-#define XVEC_STACK_OUT_BUFS 1
+// tile per (chunk, tap).
+//
+// ONE ring for both: RING_SLOTS uniform slots of SLOT_BYTES (a slab, 17 KiB; a weight tile uses the first 16 KiB), filled by
+// the producer in exactly the order the MMA warp consumes them — per chunk the slab, then one weight tile per tap — each slot
+// with its own full / empty mbarrier (a weight slot is handed back by its own MMA group's commit, a slab slot by its last
+// tap's).  What a K step costs is set by how many steps' worth of operands are in flight per SM (measured on B200, 256 x 300,
+// bf16, MMA-warp cycles per tile with separate rings of a slabs + b weight stages: 3-tap TDNN2/3 — b = 5 / 6 / 7 steps in flight:
+// 14 400 / 13 460 / 12 850 of 12 288 ideal; 1-tap TDNN4/5 — min(a, b) = 4 / 5 steps: 7 110 / 6 660 of 4 096), and two separate
+// rings cannot serve both layer shapes: the 3-tap layers want few slabs and many weight stages, the 1-tap layers want as many
+// of one as of the other.  A single FIFO of uniform slots is as deep as the shared memory allows for EITHER consumption pattern
+// (11 slots: 8.25 steps of a 3-tap layer, 5.5 of a 1-tap layer; separate rings 5 + 6: 6 and 5) and needs no drain between layers.
+// Shared memory per CTA: 1 KiB alignment slack + the ring + the TMA-store staging of the 8 epilogue warps.  bf16 activations:
+// one 2 KiB box (32 rows x 64 bytes) per warp, 12 slots; float32 activations: one 4 KiB box (32 rows x 128 bytes), 11 slots.
+#ifndef XVEC_RING_SLOTS_BF16
+#define XVEC_RING_SLOTS_BF16 12
+#define XVEC_RING_SLOTS_F32 11
+#define XVEC_STAGE_BOXES_BF16 1
 #endif
-constexpr int A_SLABS = XVEC_A_SLABS;
-constexpr int B_STAGES = XVEC_B_STAGES;
-constexpr int STACK_OUT_BUFS = XVEC_STACK_OUT_BUFS;  // store staging boxes (32 rows x 128 bytes) per epilogue warp
+template <bool kAllTf32>
+struct StackCfg {
+  static constexpr int SLOTS = kAllTf32 ? XVEC_RING_SLOTS_F32 : XVEC_RING_SLOTS_BF16;
+  static constexpr int BOX_W = kAllTf32 ? 128 : 64;                     // bytes per row of a store box (32 rows x 32 columns)
+  static constexpr int BOX_BYTES = 32 * BOX_W;
+  static constexpr int NBUF = kAllTf32 ? 1 : XVEC_STAGE_BOXES_BF16;      // store boxes in flight per epilogue warp
+  static constexpr int STAGE_BYTES = NBUF * BOX_BYTES;                   // staging per epilogue warp
+};
 constexpr int SLAB_ROWS_MAX = BM_CTA + XVEC_STACK_MAX_TAP_OFFSET;  // frame rows per slab (128 + the largest tap offset, <= 8)
 constexpr int SLAB_BYTES = SLAB_ROWS_MAX * BK_BYTES;  // 17 KiB, a multiple of 1024
-static_assert(SLAB_BYTES % 1024 == 0, "slab bases must stay 1024-byte aligned for SWIZZLE_128B");
+constexpr int SLOT_BYTES = SLAB_BYTES;
+static_assert(SLOT_BYTES % 1024 == 0 && SLOT_BYTES >= B_BYTES, "slot bases must stay 1024-byte aligned for SWIZZLE_128B and hold a weight tile");
 constexpr int SCHED_SLOTS = 8;            // work-item ring between the scheduler and the warp roles
 constexpr int CREDIT_BARS = 4;            // "tile started" barriers; the scheduler's run-ahead must stay below this (see the scheduler warp)
 constexpr int STACK_RUNAHEAD = 1;         // items a pair may hold that its producer has not started (p.runahead); measured: 1, 2, 3 give the same launch time
@@ -131,74 +146,89 @@ __host__ __device__ inline uint32_t decode_item(const StackParams& p, unsigned i
 #define XVEC_CNT(...)
 #endif
 
-// K loop of one tile on the MMA warp (leader CTA, warp-uniform; see tdnn_gemm.cu): for every channel chunk one activation slab,
-// for every tap one weight tile; the slab goes back to the producer with the last tap's commit.
-struct MmaRing {
-  int slab = 0, bst = 0;
-  uint32_t aph = 0, bph = 0, rdy = 0;  // rdy: bit0 next slab seen full, bit1 next weight tile seen full
+// Position in the operand ring: slot index + the parity of the number of times the ring has wrapped (the mbarrier phase).
+template <int kSlots>
+struct RingPos {
+  int slot = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ RingPos next() const {
+    RingPos n = *this;
+    if (++n.slot == kSlots) { n.slot = 0; n.ph ^= 1u; }
+    return n;
+  }
 };
-template <bool kTf32>
-__device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* fa, uint64_t* ea, uint64_t* fb, uint64_t* eb, uint32_t d, const StackLayer& L,
-                                         MmaRing& r, bool swap_ab, unsigned long long& c_wait, unsigned long long& c_step, bool no_a = false) {
+
+// K loop of one tile on the MMA warp (leader CTA, warp-uniform; see tdnn_gemm.cu): for every channel chunk one activation slab,
+// for every tap one weight tile, popped from the ring in the producer's push order; the slab slot goes back to the producer
+// with the last tap's commit, a weight slot with its own.
+template <int kSlots>
+struct MmaRing {
+  RingPos<kSlots> pos;  // the next slot to pop
+  uint32_t rdy = 0;     // bit0 next slab seen full, bit1 next weight tile seen full
+};
+template <bool kTf32, int kSlots>
+__device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* full, uint64_t* empty, uint32_t d, const StackLayer& L, MmaRing<kSlots>& r,
+                                         bool swap_ab, unsigned long long& c_wait, unsigned long long& c_step) {
   constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
   uint32_t acc = 0;
   for (int ch = 0; ch < L.cpt; ++ch) {
-    if (!(r.rdy & 1u) && !no_a) {
+    if (!(r.rdy & 1u)) {
       XVEC_CNT(const long long t0 = clock64();)
-      mbar_wait(&fa[r.slab], r.aph, 3);
+      mbar_wait(&full[r.pos.slot], r.pos.ph, 3);
       XVEC_CNT(c_wait += clock64() - t0;)
     }
-    if (!no_a) r.rdy &= ~1u;  // bit0 is set again by the last tap's probe of the NEXT slab
-    int slab_n = r.slab + 1;
-    uint32_t aph_n = r.aph;
-    if (slab_n == A_SLABS) { slab_n = 0; aph_n ^= 1u; }
-    if (no_a) { slab_n = r.slab; aph_n = r.aph; }  // timing experiment (debug bit 128): no slab hand-over at all
-    const uint32_t slab_addr = smem_u32(base + r.slab * SLAB_BYTES);
+    r.rdy &= ~1u;  // bit0 is set again by the last tap's probe of the NEXT slab
+    const int a_slot = r.pos.slot;
+    r.pos = r.pos.next();
+    const uint32_t slab_addr = smem_u32(base + a_slot * SLOT_BYTES);
     for (int tap = 0; tap < L.taps; ++tap) {
       if (!(r.rdy & 2u)) {
         XVEC_CNT(const long long t0 = clock64();)
-        mbar_wait(&fb[r.bst], r.bph, 3);
+        mbar_wait(&full[r.pos.slot], r.pos.ph, 3);
         XVEC_CNT(c_wait += clock64() - t0;)
       }
       tc_fence_after();
+      const int b_slot = r.pos.slot;
+      r.pos = r.pos.next();
       const uint32_t x_addr = slab_addr + static_cast<uint32_t>(L.tap_off[tap]) * BK_BYTES;  // the slab, shifted by the tap's rows
-      const uint32_t w_addr = smem_u32(base + A_SLABS * SLAB_BYTES + r.bst * B_BYTES);
+      const uint32_t w_addr = smem_u32(base + b_slot * SLOT_BYTES);
       // swap_ab: the weights are the M operand and the frames the N operand, i.e. the accumulator holds the TRANSPOSED tile
       // (TMEM lane = channel, column = frame).  Both operands are 128 rows x 128 bytes K-major, so it is only a swap.
       const uint64_t da = umma_desc_sw128(swap_ab ? w_addr : x_addr);
       const uint64_t db = umma_desc_sw128(swap_ab ? x_addr : w_addr);
-      int bst_n = r.bst + 1;
-      uint32_t bph_n = r.bph;
-      if (bst_n == B_STAGES) { bst_n = 0; bph_n ^= 1u; }
+      // what the next step pops: after the last tap the next chunk's slab (also across a tile boundary) and then its first
+      // weight tile, otherwise the next tap's weight tile
       const bool last_tap = tap == L.taps - 1;
-      const uint32_t flags = STEP_COMMIT_B | STEP_PROBE_B | ((last_tap && !no_a) ? (STEP_COMMIT_A | STEP_PROBE_A) : 0u);
+      const RingPos<kSlots> pa = r.pos;
+      const RingPos<kSlots> pb = last_tap ? r.pos.next() : r.pos;
+      const uint32_t flags = STEP_COMMIT_B | STEP_PROBE_B | (last_tap ? (STEP_COMMIT_A | STEP_PROBE_A) : 0u);
       XVEC_CNT(const long long ts = clock64();)
-      const uint32_t got = umma_step_pair<kTf32>(elect_one() ? 1u : 0u, d, da, db, idesc, acc, flags, smem_u32(&ea[r.slab]),
-                                                 smem_u32(&eb[r.bst]), smem_u32(&fa[slab_n]), aph_n, smem_u32(&fb[bst_n]), bph_n);
+      const uint32_t got = umma_step_pair<kTf32>(elect_one() ? 1u : 0u, d, da, db, idesc, acc, flags, smem_u32(&empty[a_slot]),
+                                                 smem_u32(&empty[b_slot]), smem_u32(&full[pa.slot]), pa.ph, smem_u32(&full[pb.slot]), pb.ph);
       XVEC_CNT(c_step += clock64() - ts;)
-      r.rdy = (got & 2u) | ((last_tap && !no_a) ? (got & 1u) : (no_a ? (r.rdy & 1u) : 0u));
+      r.rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
       acc = 1u;
-      r.bst = bst_n;
-      r.bph = bph_n;
     }
-    r.slab = slab_n;
-    r.aph = aph_n;
   }
 }
 
-constexpr int stack_smem_bytes() { return 1024 + A_SLABS * SLAB_BYTES + B_STAGES * B_BYTES + EPI_WARPS * STACK_OUT_BUFS * OUT_BUF_BYTES; }
+template <bool kAllTf32>
+constexpr int stack_smem_bytes() { return 1024 + StackCfg<kAllTf32>::SLOTS * SLOT_BYTES + EPI_WARPS * StackCfg<kAllTf32>::STAGE_BYTES; }
+static_assert(stack_smem_bytes<false>() <= 227 * 1024 - 1024 && stack_smem_bytes<true>() <= 227 * 1024 - 1024,
+              "operand ring + store staging (+ 1 KiB of static barriers) exceed the 227 KiB of shared memory a CTA can have");
 
 template <bool kAllTf32>
 __global__ void __launch_bounds__(STACK_THREADS, 1)
 tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant__ StackParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t fa_bar[A_SLABS], ea_bar[A_SLABS], fb_bar[B_STAGES], eb_bar[B_STAGES], tfull_bar[2], tempty_bar[2];
+  constexpr int RING_SLOTS = StackCfg<kAllTf32>::SLOTS;
+  __shared__ uint64_t full_bar[RING_SLOTS], empty_bar[RING_SLOTS], tfull_bar[2], tempty_bar[2];
   __shared__ uint64_t sfull_bar[SCHED_SLOTS], sempty_bar[SCHED_SLOTS], dep_bar[SCHED_SLOTS], credit_bar[CREDIT_BARS];
   __shared__ uint32_t sched_item[SCHED_SLOTS];
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte alignment
-  uint8_t* epi_smem = base + A_SLABS * SLAB_BYTES + B_STAGES * B_BYTES;
+  uint8_t* epi_smem = base + RING_SLOTS * SLOT_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,13 +240,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       tma_prefetch_desc(&maps.b[l]);
       if (l + 1 < p.n_layers) tma_prefetch_desc(&maps.y[l]);
     }
-    for (int s = 0; s < A_SLABS; ++s) {
-      mbar_init(&fa_bar[s], 1);  // leader's arrive.expect_tx (bytes of both CTAs)
-      mbar_init(&ea_bar[s], 1);  // leader's multicast commit (last tap of the chunk)
-    }
-    for (int s = 0; s < B_STAGES; ++s) {
-      mbar_init(&fb_bar[s], 1);
-      mbar_init(&eb_bar[s], 1);
+    for (int s = 0; s < RING_SLOTS; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx (bytes of both CTAs)
+      mbar_init(&empty_bar[s], 1);  // leader's multicast commit (a weight slot: its own MMA group; a slab slot: the chunk's last tap)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);               // leader's multicast commit
@@ -254,8 +280,8 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     // Per tile: read the work item (published by the scheduler warp while the previous tile was loading), check that this
     // CTA's dependency warp has resolved its inputs, tell the scheduler that the tile has started, then run the K loop.
-    int slab = 0, bst = 0;
-    uint32_t aph = 0, bph = 0, rdy = 0;  // rdy: bit0 next slab seen free, bit1 next weight stage seen free
+    RingPos<RING_SLOTS> pos;  // the next slot to fill
+    uint32_t rdy = 0;  // bit0 the slot of the next slab seen free, bit1 the slot of the next weight tile seen free
     XVEC_CNT(unsigned long long c_fw = 0, c_pub = 0;)
     for (int it = 0;; ++it) {
       XVEC_CNT(long long t0 = clock64();)
@@ -275,34 +301,30 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       const uint32_t slab_tx = 2u * static_cast<uint32_t>(L.slab_rows) * BK_BYTES;  // bytes of both CTAs' slabs
       // timing experiment (debug bit 32): no activation loads for n-tiles > 0 of single-tap layers, as if the m-tile's activation
       // chunks were resident in shared memory (the MMAs then read stale slabs: wrong results, right timing)
-      const bool skip_a = XVEC_SDBG(p, 32 | 128) && L.taps == 1 && nt > 0;
-      const bool no_a = XVEC_SDBG(p, 128) && L.taps == 1 && nt > 0;  // (bit 128) ... and no slab barrier hand-over either
+      const bool skip_a = XVEC_SDBG(p, 32) && L.taps == 1 && nt > 0;
       for (int ch = 0; ch < L.cpt; ++ch) {
-        if (!(rdy & 1u) && !no_a) mbar_wait(&ea_bar[slab], aph ^ 1u, 1);
-        int slab_n = slab + 1;
-        uint32_t aph_n = aph;
-        if (slab_n == A_SLABS) { slab_n = 0; aph_n ^= 1u; }
-        if (no_a) { slab_n = slab; aph_n = aph; }
-        else rdy &= ~1u;
+        if (!(rdy & 1u)) mbar_wait(&empty_bar[pos.slot], pos.ph ^ 1u, 1);
+        rdy &= ~1u;
+        const int a_slot = pos.slot;
+        pos = pos.next();
         for (int tap = 0; tap < L.taps; ++tap) {
-          if (!(rdy & 2u)) mbar_wait(&eb_bar[bst], bph ^ 1u, 1);
-          int bst_n = bst + 1;
-          uint32_t bph_n = bph;
-          if (bst_n == B_STAGES) { bst_n = 0; bph_n ^= 1u; }
+          if (!(rdy & 2u)) mbar_wait(&empty_bar[pos.slot], pos.ph ^ 1u, 1);
+          const int b_slot = pos.slot;
+          pos = pos.next();
+          // the slots the next step fills: after the last tap the next chunk's slab (also across a tile boundary) and its
+          // first weight tile, otherwise the next tap's weight tile
           const bool last_tap = tap == L.taps - 1;
-          if (skip_a && !no_a && tap == 0 && rank == 0 && elect_one()) mbar_expect_tx(&fa_bar[slab], 0);  // completes the phase with no bytes
+          const RingPos<RING_SLOTS> pa = pos;
+          const RingPos<RING_SLOTS> pb = last_tap ? pos.next() : pos;
+          if (skip_a && tap == 0 && rank == 0 && elect_one()) mbar_expect_tx(&full_bar[a_slot], 0);  // completes the phase with no bytes
           const uint32_t got = tma_step_slab(
-              elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, (tap == 0 && !skip_a) ? 1u : 0u, smem_u32(&fa_bar[slab]), mapa_u32(smem_u32(&fa_bar[slab]), 0),
-              slab_tx, smem_u32(base + slab * SLAB_BYTES), ma, ch * bke, m0, p.pol_a, smem_u32(&fb_bar[bst]),
-              mapa_u32(smem_u32(&fb_bar[bst]), 0), 2u * B_BYTES, smem_u32(base + A_SLABS * SLAB_BYTES + bst * B_BYTES), mb,
-              0, (tap * L.cpt + ch) * L.n_pad + n0, p.pol_b, smem_u32(&eb_bar[bst_n]), bph_n ^ 1u, (last_tap && !no_a) ? 1u : 0u, smem_u32(&ea_bar[slab_n]),
-              aph_n ^ 1u);
-          rdy = (got & 2u) | ((last_tap && !no_a) ? (got & 1u) : (no_a ? (rdy & 1u) : 0u));
-          bst = bst_n;
-          bph = bph_n;
+              elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, (tap == 0 && !skip_a) ? 1u : 0u, smem_u32(&full_bar[a_slot]),
+              mapa_u32(smem_u32(&full_bar[a_slot]), 0), slab_tx, smem_u32(base + a_slot * SLOT_BYTES), ma, ch * bke, m0, p.pol_a,
+              smem_u32(&full_bar[b_slot]), mapa_u32(smem_u32(&full_bar[b_slot]), 0), 2u * B_BYTES, smem_u32(base + b_slot * SLOT_BYTES), mb,
+              0, (tap * L.cpt + ch) * L.n_pad + n0, p.pol_b, smem_u32(&empty_bar[pb.slot]), pb.ph ^ 1u, last_tap ? 1u : 0u,
+              smem_u32(&empty_bar[pa.slot]), pa.ph ^ 1u);
+          rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
         }
-        slab = slab_n;
-        aph = aph_n;
       }
     }
     XVEC_CNT(if (lane == 0) {
@@ -312,7 +334,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (rank == 0) {
-      MmaRing ring;
+      MmaRing<RING_SLOTS> ring;
       unsigned long long c_full = 0, c_tempty = 0, c_step = 0, c_ring = 0;
       for (int it = 0;; ++it) {
         XVEC_CNT(const long long tr = clock64();)
@@ -327,9 +349,8 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         XVEC_CNT(c_tempty += clock64() - t0; const int dl = item & 7u; if (lane == 0) atomicAdd(p.counter + 16 + dl, static_cast<unsigned>((clock64() - t0) >> 4));)
         const uint32_t d = tmem_base + buf * BN;
         const bool pooled = static_cast<int>(item & 7u) == p.n_layers - 1;  // last layer: transposed accumulator (see the epilogue)
-        const bool no_a = XVEC_SDBG(p, 128) && L.taps == 1 && ((item >> 3) & 31u) > 0;
-        if (kAllTf32 || L.tf32) mma_tile<true>(base, fa_bar, ea_bar, fb_bar, eb_bar, d, L, ring, pooled, c_full, c_step, no_a);
-        else mma_tile<false>(base, fa_bar, ea_bar, fb_bar, eb_bar, d, L, ring, pooled, c_full, c_step, no_a);
+        if (kAllTf32 || L.tf32) mma_tile<true>(base, full_bar, empty_bar, d, L, ring, pooled, c_full, c_step);
+        else mma_tile<false>(base, full_bar, empty_bar, d, L, ring, pooled, c_full, c_step);
         if (elect_one()) umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
         __syncwarp();
         XVEC_CNT(if (lane == 0) atomicAdd(p.counter + 24 + (item & 7u), static_cast<unsigned>((clock64() - tr) >> 4));)
@@ -414,12 +435,12 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
     const int cbeg = ((warp - 2) >> 2) * (BN / 2);  // this warp's half of the tile's columns
     const int cend = cbeg + BN / 2;
-    uint8_t* out_stage = epi_smem + (warp - 2) * (STACK_OUT_BUFS * OUT_BUF_BYTES);
+    uint8_t* out_stage = epi_smem + (warp - 2) * StackCfg<kAllTf32>::STAGE_BYTES;
     // Store staging: one TMA-store box per tcgen05.ld chunk (32 rows x 32 columns).  bf16: 64-byte rows (SWIZZLE_64B), the warp's
     // 4 KiB hold two boxes, so staging chunk k+1 overlaps the store of chunk k; float32: 128-byte rows, one box.
     constexpr int BOX_W = kAllTf32 ? 128 : 64;                              // bytes per box row
     constexpr int BOX_BYTES = 32 * BOX_W;
-    constexpr int NBUF = (STACK_OUT_BUFS * OUT_BUF_BYTES) / BOX_BYTES;      // boxes in flight per warp
+    constexpr int NBUF = StackCfg<kAllTf32>::NBUF;                          // boxes in flight per warp
     constexpr int BOXES = (BN / 2) / 32;                                    // boxes (= bulk groups) per tile and warp
     int store_seq = 0;
     unsigned* pend = nullptr;  // ready counter of the last stored tile whose completion has not been published yet (warp-uniform)
@@ -658,7 +679,7 @@ XVEC_DEFINE_WATCHDOG_BINDER(bind_watchdog_stack)
 template <bool kAllTf32>
 static int launch_stack(const StackMaps& maps, const StackParams& p, int grid, cudaStream_t st) {
   static PerDeviceInit configured;  // per instantiation
-  constexpr int smem = stack_smem_bytes();
+  constexpr int smem = stack_smem_bytes<kAllTf32>();
   int rc = once_per_device(configured, [] {
     cudaError_t e = cudaFuncSetAttribute(tdnn_stack_kernel<kAllTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(XVEC_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
