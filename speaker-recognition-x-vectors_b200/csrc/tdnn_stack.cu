@@ -46,11 +46,18 @@ namespace xvec {
 // rings cannot serve both layer shapes: the 3-tap layers want few slabs and many weight stages, the 1-tap layers want as many
 // of one as of the other.  A single FIFO of uniform slots is as deep as the shared memory allows for EITHER consumption pattern
 // (11 slots: 8.25 steps of a 3-tap layer, 5.5 of a 1-tap layer; separate rings 5 + 6: 6 and 5) and needs no drain between layers.
+// Measured: MMA-warp cycles per TDNN2/3 tile 9 / 10 / 11 / 12 slots: 16 480 / 14 050 / 13 540 / 13 090; whole launch 326.8 /
+// 299.2 / 295.8 / 297.1 us (debug builds) — the launch as a whole gains 1-2 % over the separate rings, within box-to-box spread.
 // Shared memory per CTA: 1 KiB alignment slack + the ring + the TMA-store staging of the 8 epilogue warps.  bf16 activations:
-// one 2 KiB box (32 rows x 64 bytes) per warp, 12 slots; float32 activations: one 4 KiB box (32 rows x 128 bytes), 11 slots.
+// 11 slots + one 2 KiB box (32 rows x 64 bytes) per warp = 204 KiB; float32 activations: 10 slots + one 4 KiB box (32 rows x
+// 128 bytes) = 203 KiB.  NOT the 227 KiB a CTA could have: the kernels of a batch's tail (pooling finalize + segment layers)
+// must fit on the SM NEXT TO a resident CTA of the next batch's stack kernel (about 20 KiB of shared memory and 20 K registers
+// stay free), otherwise they wait for a whole stack kernel to drain — measured in round 1: ~24 us of a 325 us step.  Measured
+// here (256 x 300, bf16, us per launch on one box): 12 slots / 1 box 290.5, 11 / 2 boxes 291.9, 11 / 1 box 292.2 — the last
+// slot buys less than the co-residency it would cost.
 #ifndef XVEC_RING_SLOTS_BF16
-#define XVEC_RING_SLOTS_BF16 12
-#define XVEC_RING_SLOTS_F32 11
+#define XVEC_RING_SLOTS_BF16 11
+#define XVEC_RING_SLOTS_F32 10
 #define XVEC_STAGE_BOXES_BF16 1
 #endif
 template <bool kAllTf32>
@@ -216,6 +223,10 @@ template <bool kAllTf32>
 constexpr int stack_smem_bytes() { return 1024 + StackCfg<kAllTf32>::SLOTS * SLOT_BYTES + EPI_WARPS * StackCfg<kAllTf32>::STAGE_BYTES; }
 static_assert(stack_smem_bytes<false>() <= 227 * 1024 - 1024 && stack_smem_bytes<true>() <= 227 * 1024 - 1024,
               "operand ring + store staging (+ 1 KiB of static barriers) exceed the 227 KiB of shared memory a CTA can have");
+constexpr int STACK_SMEM_LEFT_FOR_TAIL = 20 * 1024;  // what a co-resident tail kernel may use (fc_small.cu, seg_fused.cu assert against it)
+static_assert(228 * 1024 - stack_smem_bytes<false>() - 2048 - 2 * 1024 >= STACK_SMEM_LEFT_FOR_TAIL &&
+              228 * 1024 - stack_smem_bytes<true>() - 2048 - 2 * 1024 >= STACK_SMEM_LEFT_FOR_TAIL,
+              "the stack kernel must leave room on the SM for the tail kernels of the previous batch");
 
 template <bool kAllTf32>
 __global__ void __launch_bounds__(STACK_THREADS, 1)
