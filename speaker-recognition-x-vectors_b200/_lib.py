@@ -48,7 +48,10 @@ _SIGNATURES = {
                                    c_int, c_int64, c_void_p]),
     "xvec_extract_forward": (c_int, [POINTER(LayerDesc), c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LayerDesc), c_int,
-                                     c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+                                     c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "xvec_pool_fc_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "xvec_pool_fc_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int,
+                                   c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "xvec_stack_ctrl_bytes": (c_int64, [c_int64, c_int]),
     "xvec_stack_plan": (c_int64, [c_int64, c_int, POINTER(c_int32), c_int, c_void_p, c_int64]),
     "xvec_linear_small": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_int64,

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxvec_b200.so")
-SOURCES = ["capi.cu", "tdnn_gemm.cu", "tdnn_stack.cu", "fc_small.cu", "pool.cu", "mfcc.cu"]
+SOURCES = ["capi.cu", "tdnn_gemm.cu", "tdnn_stack.cu", "fc_small.cu", "seg_fused.cu", "pool.cu", "mfcc.cu"]
 HEADERS = ["ptx.cuh", "gemm_tile.cuh", "xvec_internal.h", os.path.join("..", "..", "include", "xvec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -158,6 +158,15 @@ int64_t xvec_stack_plan(int64_t rows, int n_layers, const int32_t* n_tiles_per_l
   return stack_plan(rows, n_layers, n_tiles_per_layer_host, band, items_out_host, capacity);
 }
 
+int64_t xvec_pool_fc_workspace_bytes(int n_utts, int p, int n, int dtype) { return pool_fc_workspace_bytes(n_utts, p, n, dtype); }
+int xvec_pool_fc_fused(const float* part_dev, const int32_t* slot_start_dev, const int32_t* n_rows_dev, int n_utts, int p,
+                       const float* bn_scale_dev, const float* bn_shift_dev, const void* w_dev, int dtype, int64_t w_ld,
+                       const float* bias_dev, int n, int relu, void* out_dev, int out_dtype, int64_t out_ld, void* ws_dev, int64_t ws_bytes,
+                       void* stream) {
+  return pool_fc_dispatch(part_dev, slot_start_dev, n_rows_dev, n_utts, p, bn_scale_dev, bn_shift_dev, w_dev, dtype, w_ld, bias_dev, n, relu,
+                          out_dev, out_dtype, out_ld, ws_dev, ws_bytes, stream);
+}
+
 int xvec_linear_small(const void* x_dev, int dtype, int64_t rows, int k, int64_t x_ld, const void* w_dev, int n, int64_t w_ld,
                       const float* bias_dev, int relu, void* y_dev, int y_dtype, int64_t y_ld, void* stream) {
   return fc_small_dispatch(x_dev, dtype, rows, k, x_ld, w_dev, n, w_ld, bias_dev, relu, y_dev, y_dtype, y_ld, stream);
@@ -176,7 +185,8 @@ int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_de
                          const int32_t* utt_slot_start_dev, const int32_t* n_pool_dev, int n_utts, float* part_dev,
                          const float* bn_last_scale_dev, const float* bn_last_shift_dev, float* pooled_dev, void* pooled_lp_dev,
                          const XvecLayerDesc* fc, int n_fc, void* fc_tmp_dev, void* splitk_ws_dev, int64_t splitk_ws_bytes,
-                         float* out_dev, int64_t out_ld, void* ctrl_dev, int64_t ctrl_bytes, void* stream) {
+                         float* out_dev, int64_t out_ld, void* tail_ws_dev, int64_t tail_ws_bytes, void* ctrl_dev, int64_t ctrl_bytes,
+                         void* stream) {
   if (!tdnn || n_tdnn < 2 || !fc || n_fc < 1 || n_fc > 2) return set_error(XVEC_E_ARG, "need >= 2 TDNN layers and 1 or 2 segment layers");
   if (!x_dev || !act0_dev || !act1_dev || !pooled_dev || !out_dev) return set_error(XVEC_E_ARG, "null pointer argument");
   if (n_fc == 2 && !fc_tmp_dev) return set_error(XVEC_E_ARG, "fc_tmp_dev is NULL");
@@ -208,6 +218,24 @@ int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_de
   if (skip_tail >= 2) return XVEC_OK;
 #endif
   const int fc_in_dtype = fc[0].dtype;
+  int first_fc = 0;
+  const void* a = nullptr;
+  int64_t a_ld = 0;
+  if (fc[0].w_plain_dev && tail_ws_dev && use_fc_small() && fc[0].cin == 2 * last.n &&
+      pool_fc_supported(n_utts, last.n, fc[0].n, fc_in_dtype, fc[0].cin, fc[0].w_plain_dev) &&
+      tail_ws_bytes >= pool_fc_workspace_bytes(n_utts, last.n, fc[0].n, fc_in_dtype)) {
+    // the tail in ONE launch: pooling finalize + first segment layer (seg_fused.cu); the pooled matrix is never materialised
+    const bool final_layer = n_fc == 1;
+    void* y = final_layer ? static_cast<void*>(out_dev) : fc_tmp_dev;
+    const int y_dtype = final_layer ? XVEC_F32 : fc[1].dtype;
+    const int64_t y_ld = final_layer ? out_ld : fc[0].n;
+    rc = pool_fc_dispatch(part_dev, utt_slot_start_dev, n_pool_dev, n_utts, last.n, bn_last_scale_dev, bn_last_shift_dev, fc[0].w_plain_dev,
+                          fc_in_dtype, fc[0].cin, fc[0].bias_dev, fc[0].n, final_layer ? 0 : 1, y, y_dtype, y_ld, tail_ws_dev, tail_ws_bytes, stream);
+    if (rc) return rc;
+    first_fc = 1;
+    a = y;
+    a_ld = y_ld;
+  } else {
   if (fc_in_dtype == XVEC_BF16 && !pooled_lp_dev) return set_error(XVEC_E_ARG, "pooled_lp_dev is required for bf16 segment layers");
   rc = xvec_pool_finalize(part_dev, utt_slot_start_dev, n_pool_dev, n_utts, last.n, bn_last_scale_dev, bn_last_shift_dev, nullptr, pooled_dev,
                           fc_in_dtype == XVEC_BF16 ? pooled_lp_dev : nullptr, XVEC_BF16, 2 * static_cast<int64_t>(last.n), stream);
@@ -215,9 +243,10 @@ int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_de
 #ifdef XVEC_DEBUG
   if (skip_tail >= 1) return XVEC_OK;
 #endif
-  const void* a = fc_in_dtype == XVEC_BF16 ? pooled_lp_dev : static_cast<const void*>(pooled_dev);
-  int64_t a_ld = 2 * static_cast<int64_t>(last.n);
-  for (int i = 0; i < n_fc; ++i) {
+  a = fc_in_dtype == XVEC_BF16 ? pooled_lp_dev : static_cast<const void*>(pooled_dev);
+  a_ld = 2 * static_cast<int64_t>(last.n);
+  }
+  for (int i = first_fc; i < n_fc; ++i) {
     const bool final_layer = i == n_fc - 1;
     void* y = final_layer ? static_cast<void*>(out_dev) : fc_tmp_dev;
     const int y_dtype = final_layer ? XVEC_F32 : fc[i + 1].dtype;

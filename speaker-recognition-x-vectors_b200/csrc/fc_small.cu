@@ -97,7 +97,7 @@ fc_small_kernel(const uint8_t* __restrict__ x, long long ldx_bytes, const uint8_
       for (int e = 0; e < 2; ++e) {
         if (col + e >= N) continue;
         float v = acc[t][2 * h + e] + (bias ? bias[col + e] : 0.f);
-        if (relu) v = fmaxf(v, 0.f);
+        if (relu) v = v < 0.f ? 0.f : v;  // keeps NaN like torch.relu (fmaxf would turn it into 0)
         if (kOutBf16) reinterpret_cast<__nv_bfloat16*>(y)[static_cast<long long>(row) * ldy + col + e] = __float2bfloat16_rn(v);
         else reinterpret_cast<float*>(y)[static_cast<long long>(row) * ldy + col + e] = v;
       }

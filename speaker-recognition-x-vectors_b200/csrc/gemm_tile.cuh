@@ -23,6 +23,10 @@ constexpr int TMEM_COLS = 512;
 constexpr int OUT_BUF_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes
 constexpr int OUT_BUFS = 2;              // staging boxes per epilogue warp (TMA stores in flight)
 
+// ReLU that keeps NaN like torch.relu (fmaxf(NaN, 0) is 0): the std of a single-frame utterance is NaN (torch.std, main.py:61) and
+// has to stay NaN through relu(segment6) (main.py:72, 89).
+__device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.f ? 0.f : v; }
+
 // {lo, hi} floats -> packed bf16x2 (lo in the low half), round-to-nearest; the _relu form clamps negatives to 0.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

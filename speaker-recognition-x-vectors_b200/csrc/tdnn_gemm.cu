@@ -294,7 +294,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               if (p.relu && kEpi != EPI_STORE_BF16) {  // bf16 output: ReLU is folded into the convert below
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+                for (int j = 0; j < 32; ++j) o[j] = relu_keep_nan(o[j]);
               }
             } else {
               const float4* sp = reinterpret_cast<const float4*>(p.scale + col0);
@@ -306,7 +306,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float4 sh = __ldg(hp + (j4 >> 2));
                 float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 0]), __uint_as_float(v[j4 + 1])), make_float2(bb.x, bb.y));
                 float2 d = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), make_float2(bb.z, bb.w));
-                if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); d.x = fmaxf(d.x, 0.f); d.y = fmaxf(d.y, 0.f); }
+                if (p.relu) { a.x = relu_keep_nan(a.x); a.y = relu_keep_nan(a.y); d.x = relu_keep_nan(d.x); d.y = relu_keep_nan(d.y); }
                 a = __ffma2_rn(a, make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
                 d = __ffma2_rn(d, make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
                 o[j4 + 0] = a.x; o[j4 + 1] = a.y; o[j4 + 2] = d.x; o[j4 + 3] = d.y;
@@ -349,7 +349,7 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.n) dst[j] = __float2bfloat16_rn(cvt_relu ? fmaxf(o[j], 0.f) : o[j]);
+                  if (col0 + j < p.n) dst[j] = __float2bfloat16_rn(cvt_relu ? relu_keep_nan(o[j]) : o[j]);
               } else {
                 float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
@@ -402,7 +402,7 @@ splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, int rows, int row
     float a = 0.f;
     for (int s = 0; s < ksplit; ++s) a += ws[(static_cast<size_t>(s) * rows_pad + r) * ws_ld + c];
     if (bias) a += bias[c];
-    if (relu) a = fmaxf(a, 0.f);
+    if (relu) a = a < 0.f ? 0.f : a;  // keeps NaN like torch.relu
     if (scale) a = fmaf(a, scale[c], shift[c]);
     if (out_bf16)
       reinterpret_cast<__nv_bfloat16*>(out)[static_cast<size_t>(r) * ldo + c] = __float2bfloat16_rn(a);

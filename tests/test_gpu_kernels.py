@@ -350,3 +350,62 @@ print("watchdog", code, "after reset", lib.xvec_watchdog_code(), flush=True)
     env = dict(os.environ, XVEC_LIB=dbg_lib, XVEC_STACK_DBG="0")
     r = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=300)
     assert "watchdog 0 after reset 0" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("n_utts,p,n,relu,out_dtype", [(256, 1500, 512, False, torch.float32), (37, 1500, 512, True, torch.bfloat16),
+                                                        (5, 200, 96, False, torch.float32), (300, 1500, 1211 + 1, True, torch.float32)])
+def test_pool_fc_fused_matches_finalize_plus_linear(xb, dtype, n_utts, p, n, relu, out_dtype):
+    """xvec_pool_fc_fused (pooling finalize + first segment layer in one launch, split-K with an in-kernel fixed-order reduction)
+    against float64 of main.py:59-63 + :45: statistics from the partial sums exactly as xvec_pool_finalize defines them, then the
+    affine layer on the statistics rounded to the operand dtype.  Also: bit-identical when repeated on the same workspace (the
+    arrival counters return to zero), NaN rows of single-frame utterances stay confined to their utterance."""
+    g = torch.Generator().manual_seed(n_utts * 3 + p)
+    n_rows = torch.randint(2, 900, (n_utts,), generator=g).int()
+    n_rows[0] = 1  # a single pooled frame: unbiased std is NaN (torch.std), and only this utterance's outputs may be NaN
+    slots = (n_rows + 127) // 128 + torch.randint(0, 2, (n_utts,), generator=g).int()
+    slot_start = torch.cat([torch.zeros(1, dtype=torch.int32), torch.cumsum(slots, 0).int()])
+    n_slots = int(slot_start[-1])
+    # partial sums of r >= 0 (post-ReLU activations): S, Q per slot such that the variance is positive
+    r_mean = torch.rand(n_utts, p, generator=g) + 0.1
+    r_var = 0.05 + torch.rand(n_utts, p, generator=g)
+    part = torch.zeros(n_slots, 2, p)
+    for u in range(n_utts):
+        k = int(slots[u])
+        nr = int(n_rows[u])
+        S = r_mean[u] * nr
+        Q = (r_var[u] * max(nr - 1, 1) + r_mean[u] ** 2 * nr)
+        w = torch.rand(k, 1, generator=g) + 0.5
+        w = w / w.sum()
+        part[int(slot_start[u]):int(slot_start[u]) + k, 0] = w * S
+        part[int(slot_start[u]):int(slot_start[u]) + k, 1] = w * Q
+    scale = torch.randn(p, generator=g)
+    shift = torch.randn(p, generator=g)
+    W = (torch.randn(n, 2 * p, generator=g) / (2 * p) ** 0.5).to(dtype)
+    b = torch.randn(n, generator=g)
+    # float64 reference from the same partials
+    S = torch.stack([part[int(slot_start[u]):int(slot_start[u + 1]), 0].double().sum(0) for u in range(n_utts)])
+    Q = torch.stack([part[int(slot_start[u]):int(slot_start[u + 1]), 1].double().sum(0) for u in range(n_utts)])
+    nr = n_rows.double()[:, None]
+    mean = S / nr * scale.double() + shift.double()
+    std = scale.double().abs() * torch.sqrt(((Q - S * S / nr) / (nr - 1)).clamp_min(0))
+    x = torch.cat([mean, std], 1).to(dtype).double()  # the kernel feeds the tensor cores with the statistics in the operand dtype
+    ref = x @ W.double().t() + b.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    ws = torch.zeros(xb._lib.load().xvec_pool_fc_workspace_bytes(n_utts, p, n, xb._lib.dtype_code(dtype)), dtype=torch.uint8, device="cuda")
+    args = (part.cuda(), slot_start.cuda(), n_rows.cuda(), p, W.cuda(), b.cuda(), scale.cuda(), shift.cuda())
+    got = xb.ops.pool_fc_fused(*args, relu=relu, out_dtype=out_dtype, workspace=ws)
+    again = xb.ops.pool_fc_fused(*args, relu=relu, out_dtype=out_dtype, workspace=ws)
+    assert torch.equal(got.view(torch.int16 if out_dtype == torch.bfloat16 else torch.int32), again.view(torch.int16 if out_dtype == torch.bfloat16 else torch.int32))
+    got = got.double().cpu()
+    assert got.shape == ref.shape
+    assert torch.isnan(got[0]).all() and torch.isfinite(got[1:]).all()  # also through ReLU: torch.relu keeps NaN
+    # bf16 operands: the kernel rounds float64 -> float32 -> bf16, the reference float64 -> bf16; a statistic on a rounding
+    # boundary may differ by one bf16 ulp (4e-3 of one of 3000 terms)
+    tol = 1e-2 if out_dtype == torch.bfloat16 else (3e-4 if dtype == torch.bfloat16 else 1e-3)
+    assert ((got[1:] - ref[1:]).abs().max() / ref[1:].abs().max()).item() < tol
+    # and the unfused pair of kernels gives the same answer up to float32 summation order
+    pooled = xb.ops.pool_finalize(args[0], args[1], args[2], p, scale.cuda(), shift.cuda())
+    unfused = xb.ops.linear_small(pooled.to(dtype), W.cuda(), b.cuda(), relu=relu, out_dtype=out_dtype).double().cpu()
+    assert ((got[1:] - unfused[1:]).abs().max() / ref[1:].abs().max()).item() < (1e-2 if out_dtype == torch.bfloat16 else 3e-4 if dtype == torch.bfloat16 else 2e-3)
