@@ -100,9 +100,18 @@ static bool use_fc_small() {
   static const bool v = env_switch_on("XVEC_FC_SMALL");
   return v;
 }
+// XVEC_TAIL_FUSED=1  the tail of xvec_extract_forward runs as ONE launch (xvec_pool_fc_fused) instead of xvec_pool_finalize +
+//                     xvec_linear_small.  Measured on B200 (256 utterances, warm L2, ncu --cache-control none): 7.9 + 23.3 us
+//                     unfused vs 37.9 us fused in bf16 (41.8 + 7.9 vs 54.8 in TF32) — one launch less, but every 16-utterance CTA
+//                     re-reads its slice of W (89 MB of L2 traffic against 55 MB), so the two-launch tail stays the default.
+static bool use_fused_tail() {
+  static const bool v = getenv("XVEC_TAIL_FUSED") && getenv("XVEC_TAIL_FUSED")[0] == '1';
+  return v;
+}
 #else
 static constexpr bool use_stack_kernel() { return true; }
 static constexpr bool use_fc_small() { return true; }
+static constexpr bool use_fused_tail() { return false; }
 #endif
 
 }  // namespace xvec
@@ -221,10 +230,11 @@ int xvec_extract_forward(const XvecLayerDesc* tdnn, int n_tdnn, const void* x_de
   int first_fc = 0;
   const void* a = nullptr;
   int64_t a_ld = 0;
-  if (fc[0].w_plain_dev && tail_ws_dev && use_fc_small() && fc[0].cin == 2 * last.n &&
+  if (use_fused_tail() && fc[0].w_plain_dev && tail_ws_dev && use_fc_small() && fc[0].cin == 2 * last.n &&
       pool_fc_supported(n_utts, last.n, fc[0].n, fc_in_dtype, fc[0].cin, fc[0].w_plain_dev) &&
       tail_ws_bytes >= pool_fc_workspace_bytes(n_utts, last.n, fc[0].n, fc_in_dtype)) {
     // the tail in ONE launch: pooling finalize + first segment layer (seg_fused.cu); the pooled matrix is never materialised
+    // (debug-build A/B switch only: measured slower than the two launches, see use_fused_tail)
     const bool final_layer = n_fc == 1;
     void* y = final_layer ? static_cast<void*>(out_dev) : fc_tmp_dev;
     const int y_dtype = final_layer ? XVEC_F32 : fc[1].dtype;
