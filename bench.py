@@ -43,11 +43,12 @@ SEG6_FLOPS = 3_072_000
 LAUNCHES_PER_BATCH = 3  # tdnn_stack_kernel, pool_finalize_kernel, fc_small_kernel (segment6)
 LONG_BATCHES = 2048     # the "long" legs: ~0.6 s of bf16 work per GPU
 WORKLOAD = "c2: 1024 x 3 s utterances (300 x 24 MFCC) per step and GPU as 4 batches of 256, x_vec_extract_layer 6"
-NCU_TENSOR_PIPE = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 73.5, "file": "profiles/r01_v13_ncu_full_summary.txt",
-                   "note": "ncu --set full capture of one tdnn_stack_kernel launch (cold, serialised, 1.62 GHz)"}
+NCU_TENSOR_PIPE = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 71.7, "file": "profiles/r02_stack_ncu_full_summary.txt",
+                   "note": "ncu --set full capture of one tdnn_stack_kernel launch (cold, serialised, 298.6 us at 1.63 GHz); ~7 % of the issued "
+                           "MMA work is padding (don't-care rows of the flat layout, N 1500 -> 1536, K 120 -> 128)"}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tdnn_stack_kernel launch on this workload (ncu --set full; see profiles/README.md)
-STACK_DRAM_BYTES = {"bf16": 204429312, "tf32": None}
-STACK_DRAM_SOURCE = "profiles/r01_v13_ncu_full_summary.txt"
+STACK_DRAM_BYTES = {"bf16": 179915776, "tf32": None}  # 17.6 MB read + 162.3 MB written (final contents of the activation buffers)
+STACK_DRAM_SOURCE = "profiles/r02_stack_ncu_full_summary.txt"
 
 
 def flops_per_utt(t):

@@ -157,3 +157,45 @@ def test_plda_fast_scoring_equals_model_definition():
     same = po.trial_scores(np.vstack([a, b]), np.arange(200), 200 + np.arange(200), mean, F, S)
     diff = po.trial_scores(np.vstack([a, b]), np.arange(200), 200 + np.roll(np.arange(200), 1), mean, F, S)
     assert same.mean() > diff.mean() + 1.0
+
+
+def test_mfcc_oracle_pieces_agree_with_torchaudio():
+    """INDEPENDENT (not pinning) evidence for oracle/mfcc_oracle.py — python_speech_features itself is not available offline, so
+    row f4 stays 'parity unpinned'.  torchaudio ships the same textbook pieces written by other people:
+      * DCT-II (ortho): torchaudio.functional.create_dct == dct_matrix, to rounding;
+      * sinusoidal lifter: torchaudio.compliance.kaldi._get_lifter_coeffs == lifter_weights, to rounding;
+      * HTK mel scale + triangular filters: torchaudio places the triangle corners at exact frequencies, python_speech_features
+        (and the oracle) on floor()ed FFT bins, so the banks cannot be equal — they must agree in centre frequency to one bin
+        and overlap to > 0.9 (cosine between corresponding filters);
+      * the whole chain with torchaudio's pieces substituted for the DCT and the lifter gives the oracle's MFCCs to 1e-5."""
+    torchaudio = pytest.importorskip("torchaudio")
+    import torchaudio.functional as AF
+    from torchaudio.compliance import kaldi
+    from oracle import mfcc_oracle as mo
+    dct = AF.create_dct(mo.NUMCEP, mo.NFILT, norm="ortho").double().numpy().T          # (numcep, nfilt)
+    assert np.abs(dct - mo.dct_matrix()).max() < 5e-6                                    # torchaudio builds a float32 table
+    lift = kaldi._get_lifter_coeffs(mo.NUMCEP, float(mo.CEPLIFTER)).double().numpy()
+    assert np.abs(lift - mo.lifter_weights()).max() < 1e-5
+    fb_ta = AF.melscale_fbanks(mo.NFFT // 2 + 1, 0.0, mo.SAMPLE_RATE / 2.0, mo.NFILT, mo.SAMPLE_RATE, norm=None, mel_scale="htk").double().numpy().T
+    fb = mo.filterbank()
+    assert fb.shape == fb_ta.shape == (mo.NFILT, mo.NFFT // 2 + 1)
+    assert np.abs(fb.argmax(1) - fb_ta.argmax(1)).max() <= 1                             # same centre bins (+- the floor)
+    cos = (fb * fb_ta).sum(1) / (np.linalg.norm(fb, axis=1) * np.linalg.norm(fb_ta, axis=1))
+    assert cos.min() > 0.9, cos.min()
+    # mel scale itself: the filter edges in Hz are the HTK formula's
+    edges_hz = mo.mel2hz(np.linspace(mo.hz2mel(0.0), mo.hz2mel(8000.0), mo.NFILT + 2))
+    m_ta = 2595.0 * np.log10(1.0 + edges_hz / 700.0)
+    assert np.abs(np.diff(m_ta) - np.diff(m_ta).mean()).max() < 1e-9                     # equally spaced on torchaudio's HTK mel axis
+    # the chain with torchaudio's DCT / lifter substituted
+    rng = np.random.default_rng(0)
+    sig = rng.standard_normal(16000)
+    ref = mo.mfcc_np(sig)
+    y = np.append(sig[0], sig[1:] - mo.PREEMPH * sig[:-1])
+    nf = mo.num_frames(len(y))
+    padded = np.zeros((nf - 1) * mo.FRAME_STEP + mo.FRAME_LEN)
+    padded[: len(y)] = y
+    frames = padded[np.arange(mo.FRAME_LEN)[None, :] + mo.FRAME_STEP * np.arange(nf)[:, None]]
+    pspec = np.abs(np.fft.rfft(frames, mo.NFFT)) ** 2 / mo.NFFT
+    ceps = np.log(pspec @ fb.T) @ dct.T * lift[None, :]
+    ceps[:, 0] = np.log(pspec.sum(1))
+    assert np.abs(ceps - ref).max() < 1e-5 * np.abs(ref).max()
