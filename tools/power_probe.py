@@ -13,6 +13,7 @@ m = xvec_b200.XVectorModel(precision=sys.argv[1] if len(sys.argv) > 1 else "bf16
 B, T, NRES = 256, 300, 24
 x = torch.randn(NRES, B * T, 24, device="cuda")
 lengths = [T] * B
+BAND = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # m-tiles per scheduling band (0 = the library's choice)
 lay = m._layout_for(lengths); sc = m._scratch_for(0); sc.ensure(lay.rows, lay.n_slots, lay.n_utts)
 pipe = m._pipeline(); part = sc.part[: lay.n_slots]
 flops = B * sum(f * (T - l) for f, l in zip([122880, 1572864, 1572864, 524288, 1536000], [4, 8, 14, 14, 14]))
@@ -30,7 +31,7 @@ def run(n):
         xs = x[it % NRES]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl)
+        ops.tdnn_stack(pipe["tdnn"], pipe["n_tdnn"], xs, sc.act[0], sc.act[1], lay.row_utt, lay.blk_slot_base, part, sc.ctrl, band=BAND)
         e1.record(); evs.append((e0, e1))
     torch.cuda.synchronize()
     return [a.elapsed_time(b) for a, b in evs]
