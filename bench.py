@@ -46,9 +46,12 @@ WORKLOAD = "c2: 1024 x 3 s utterances (300 x 24 MFCC) per step and GPU as 4 batc
 NCU_TENSOR_PIPE = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 71.7, "file": "profiles/r02_stack_ncu_full_summary.txt",
                    "note": "ncu --set full capture of one tdnn_stack_kernel launch (cold, serialised, 298.6 us at 1.63 GHz); ~7 % of the issued "
                            "MMA work is padding (don't-care rows of the flat layout, N 1500 -> 1536, K 120 -> 128)"}
+NCU_TENSOR_PIPE_TF32 = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 74.6, "file": "profiles/r02_pool_tf32_ncu_full_summary.txt",
+                        "note": "ncu --set full capture of one tdnn_stack_kernel<tf32> launch (556.5 us)"}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tdnn_stack_kernel launch on this workload (ncu --set full; see profiles/README.md)
-STACK_DRAM_BYTES = {"bf16": 179915776, "tf32": None}  # 17.6 MB read + 162.3 MB written (final contents of the activation buffers)
-STACK_DRAM_SOURCE = "profiles/r02_stack_ncu_full_summary.txt"
+STACK_DRAM_BYTES = {"bf16": 179915776,   # 17.6 MB read + 162.3 MB written (final contents of the activation buffers)
+                    "tf32": 695182576}   # 120.9 MB read + 574.3 MB written: float32 activations of a band do not fit in L2
+STACK_DRAM_SOURCE = {"bf16": "profiles/r02_stack_ncu_full_summary.txt", "tf32": "profiles/r02_pool_tf32_ncu_full_summary.txt"}
 
 
 def flops_per_utt(t):
@@ -406,9 +409,9 @@ def roofline_object(precision, burst_ms, burst_clk, sus_ms, sus_clk, n_launch, t
             "bound": "tensor", "achieved": pick["achieved"], "peak": pick["peak"], "unit": "TFLOP/s", "frac": pick["frac"],
             "regime": regime, "regime_note": "frac/achieved/peak repeat the regime the K-step `value` leg of this run was in "
                                              "(burst unless its timed region saw sw_power_cap for most of its length)",
-            "traffic": STACK_DRAM_BYTES.get(precision), "traffic_source": STACK_DRAM_SOURCE if STACK_DRAM_BYTES.get(precision) else None,
+            "traffic": STACK_DRAM_BYTES.get(precision), "traffic_source": STACK_DRAM_SOURCE.get(precision),
             "algorithmic_flops_per_launch": fl, "peak_source": peak_source, "burst": burst, "sustained": sus,
-            "ncu": NCU_TENSOR_PIPE if precision == "bf16" else None}
+            "ncu": NCU_TENSOR_PIPE if precision == "bf16" else NCU_TENSOR_PIPE_TF32}
 
 
 def run_b200(args, rank, world, local_rank):
@@ -817,7 +820,7 @@ def pooling_roofline(model, dev, peaks):
     del a
     return {"kernel": "stats_pool_partial_kernel + pool_finalize_kernel (standalone stat_pool, 64 x 5986 x 1500 fp32)", "bound": "hbm",
             "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": 2441932472,  # dram__bytes_read+write of stats_pool_partial_kernel per launch, profiles/r01_v5_ncu_pool_summary.txt
+            "traffic": 2448198720,  # dram__bytes_read + write of stats_pool_partial_kernel per launch (2.437 GB + 11.6 MB), profiles/r02_pool_tf32_ncu_full_summary.txt
             "algorithmic_bytes": nbytes, "ms": ms, "peak_source": f"{peaks['source']} hbm_gbs"}
 
 
