@@ -86,6 +86,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   }
 }
 
+// The same by 32-bit shared-memory address: the hot loops keep barrier / ring base addresses in registers — taking the address
+// of a __shared__ object costs an S2UR + ULEA each time (the shared window of a CTA in a cluster), three times per K step.
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity, uint32_t code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar_addr, parity)) {
+    if (++spins > (1u << 26)) watchdog_trip(code);
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+
 // Arrive on the same-offset barrier of another CTA of the cluster (shared::cluster address from mapa).
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {
   uint32_t r;
@@ -284,9 +307,13 @@ __device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, u
 // One K step of the CTA-pair mainloop as a single instruction group, issued by a converged warp:
 //   - the elected lane issues the four tcgen05.mma of this 128-byte K chunk (32 bytes of K each) and the commits that
 //     release the operand stages,
-//   - then every lane probes (try_wait) the barriers the NEXT step will need.  try_wait may suspend the thread until the
-//     phase completes or a system time limit expires, so it has to come AFTER the issue: in front of it, it delayed the
-//     MMAs of a stage that was ready until the following stage had landed (measured: 336 -> 3xx us for the stack kernel).
+//   - every lane probes the barriers the NEXT step will need with test_wait (non-blocking) BEFORE the issue, so that the
+//     ~100-150 cycles the probe takes to answer overlap the issue work instead of sitting between two steps of a single warp
+//     (round 2: the MMA warp's own instruction stream, ~600-750 cycles per K step against 512 of tensor work, is what the
+//     K = 512 tiles wait for).  try_wait is not usable there: it may suspend the thread until the phase completes or a time
+//     limit expires, which in front of the issue delayed the MMAs of a stage that was ready until the following stage had
+//     landed.  A probe that answers "not yet" leaves its bit clear; the caller then waits (try_wait loop) at the top of the
+//     next step.
 // Returns bit0 = next A barrier already complete, bit1 = next B barrier already complete.
 // One producer step of the CTA-pair mainloop as a single instruction group (converged warp): the elected lane arms the
 // leader's full barrier (leader only) and issues the two tensor loads of this stage, then the warp probes (try_wait, which may
@@ -319,16 +346,18 @@ __device__ __forceinline__ uint32_t tma_step_pair(uint32_t elected, uint32_t is_
 // Producer step of the slab pipeline (tdnn_stack.cu) as one instruction group (converged warp): the elected lane arms the
 // leader's barriers and issues [the activation slab load of a new channel chunk, if do_a] + the weight-tile load of this
 // (chunk, tap); then the warp probes (try_wait, may suspend) the empty barrier of the next weight stage and, if probe_a, of
-// the next slab.  Returns bit0 = next slab seen free, bit1 = next weight stage seen free.
+// the next slab.  Returns bit0 = next slab seen free, bit1 = next weight stage seen free.  (Round 2: the probes are test_wait,
+// issued before the loads, for the reason given at umma_step_pair.)
 __device__ __forceinline__ uint32_t tma_step_slab(uint32_t elected, uint32_t is_leader, uint32_t do_a, uint32_t fa_local, uint32_t fa_leader,
                                                   uint32_t a_tx, uint32_t smem_a, const CUtensorMap* map_a, int32_t a0, int32_t a1,
                                                   uint64_t pol_a, uint32_t fb_local, uint32_t fb_leader, uint32_t b_tx, uint32_t smem_b,
                                                   const CUtensorMap* map_b, int32_t b0, int32_t b1, uint64_t pol_b, uint32_t probe_b_bar,
-                                                  uint32_t probe_b_par, uint32_t probe_a, uint32_t probe_a_bar, uint32_t probe_a_par) {
+                                                  uint32_t probe_b_par, uint32_t probe_a, uint32_t probe_a_bar, uint32_t probe_a_par,
+                                                  uint32_t do_b = 1u) {
   uint32_t rdy;
   asm volatile(
       "{\n\t"
-      ".reg .pred pe, pl, pa, pla, ppa, pwa, pwb;\n\t"
+      ".reg .pred pe, pl, pa, pla, ppa, pwa, pwb, pb;\n\t"
       ".reg .b32 ra, rb;\n\t"
       "setp.ne.b32 pe, %1, 0;\n\t"
       "setp.ne.b32 pl, %2, 0;\n\t"
@@ -336,14 +365,16 @@ __device__ __forceinline__ uint32_t tma_step_slab(uint32_t elected, uint32_t is_
       "setp.ne.b32 pa, %3, 0;\n\t"
       "and.pred pla, pa, pl;\n\t"
       "and.pred pa, pa, pe;\n\t"
+      "setp.ne.b32 pb, %25, 0;\n\t"
+      "and.pred pb, pb, pe;\n\t"
       "setp.ne.b32 ppa, %22, 0;\n\t"
       "setp.ne.b32 pwa, 0, 0;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pwb, [%20], %21;\n\t"
+      "@ppa mbarrier.test_wait.parity.shared::cta.b64 pwa, [%23], %24;\n\t"
       "@pla mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %6;\n\t"
       "@pa cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%7], [%8, {%9, %10}], [%5], %11;\n\t"
       "@pl mbarrier.arrive.expect_tx.shared::cta.b64 _, [%12], %14;\n\t"
-      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%15], [%16, {%17, %18}], [%13], %19;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 pwb, [%20], %21;\n\t"
-      "@ppa mbarrier.try_wait.parity.shared::cta.b64 pwa, [%23], %24;\n\t"
+      "@pb cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%15], [%16, {%17, %18}], [%13], %19;\n\t"
       "selp.u32 ra, 1, 0, pwa;\n\t"
       "selp.u32 rb, 2, 0, pwb;\n\t"
       "or.b32 %0, ra, rb;\n\t"
@@ -352,7 +383,7 @@ __device__ __forceinline__ uint32_t tma_step_slab(uint32_t elected, uint32_t is_
       : "r"(elected), "r"(is_leader), "r"(do_a), "r"(fa_local), "r"(fa_leader), "r"(a_tx), "r"(smem_a),
         "l"(reinterpret_cast<uint64_t>(map_a)), "r"(a0), "r"(a1), "l"(pol_a), "r"(fb_local), "r"(fb_leader), "r"(b_tx), "r"(smem_b),
         "l"(reinterpret_cast<uint64_t>(map_b)), "r"(b0), "r"(b1), "l"(pol_b), "r"(probe_b_bar), "r"(probe_b_par), "r"(probe_a),
-        "r"(probe_a_bar), "r"(probe_a_par)
+        "r"(probe_a_bar), "r"(probe_a_par), "r"(do_b)
       : "memory");
   return rdy;
 }
@@ -379,6 +410,8 @@ __device__ __forceinline__ uint32_t umma_step_pair(uint32_t elected, uint32_t tm
       "and.b32 f, %7, 8;\n\tsetp.ne.b32 ppb, f, 0;\n\t"                                                          \
       "setp.ne.b32 pwa, 0, 0;\n\t"                                                                                \
       "setp.ne.b32 pwb, 0, 0;\n\t"                                                                                \
+      "@ppa mbarrier.test_wait.parity.shared::cta.b64 pwa, [%10], %11;\n\t"                                       \
+      "@ppb mbarrier.test_wait.parity.shared::cta.b64 pwb, [%12], %13;\n\t"                                       \
       "add.u64 a1, %3, 2;\n\tadd.u64 a2, %3, 4;\n\tadd.u64 a3, %3, 6;\n\t"                                      \
       "add.u64 b1, %4, 2;\n\tadd.u64 b2, %4, 4;\n\tadd.u64 b3, %4, 6;\n\t"                                      \
       "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%2], %3, %4, %5, pacc;\n\t"                                   \
@@ -389,8 +422,6 @@ __device__ __forceinline__ uint32_t umma_step_pair(uint32_t elected, uint32_t tm
       "and.b32 f, %7, 1;\n\tsetp.ne.b32 pca, f, 0;\n\tand.pred pca, pca, pe;\n\t"                               \
       "@pcb tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], mk;\n\t" \
       "@pca tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], mk;\n\t" \
-      "@ppa mbarrier.try_wait.parity.shared::cta.b64 pwa, [%10], %11;\n\t"                                        \
-      "@ppb mbarrier.try_wait.parity.shared::cta.b64 pwb, [%12], %13;\n\t"                                        \
       "selp.u32 ra, 1, 0, pwa;\n\t"                                                                               \
       "selp.u32 rb, 2, 0, pwb;\n\t"                                                                               \
       "or.b32 %0, ra, rb;\n\t"                                                                                    \

@@ -139,12 +139,14 @@ __host__ __device__ inline uint32_t decode_item(const StackParams& p, unsigned i
 // tests/test_gpu_kernels.py::test_watchdog_code_is_readable uses), 4 skip the proxy fences (results are then undefined; timing
 // experiments only), 8 short watchdog limit for the dependency spin (2^12 polls instead of 2^24), 16 the dependency watchdog
 // reports its code and stops waiting instead of trapping (a trap is an Xid event on the box; the test only needs the code),
-// 32 / 64 timing experiments: no activation loads for n-tiles > 0 of single-tap layers / no epilogue work at all.
+// 32 / 64 / 128 timing experiments: no activation loads for n-tiles > 0 of single-tap layers / no epilogue work at all / no weight
+// loads for those tiles.
 // Debug builds also accumulate counters in the spare words of the control block (read by tools/stack_bench.py; units of 64
 // cycles unless stated): 1 tiles whose dependency warp had to spin on a flag (count), 2 flag polls (count), 3 producer waiting
 // for its dependency warp, 4 producer waiting for the work item, 5 MMA warp waiting for operands (explicit waits only),
 // 6 MMA warp waiting for a free accumulator buffer, 8 / 9 lifetime of CTA 0 in cycles / nanoseconds (SM clock), 10 time inside
-// the tcgen05 step, 11 MMA warp waiting for the work item, 16.. / 24.. per layer: accumulator wait / whole tile (units of 16).
+// the tcgen05 step, 11 MMA warp waiting for the work item, per layer (units of 16): 16.. accumulator wait, 24.. whole tile, 32.. work-item
+// wait, 40.. K loop, 48.. explicit operand waits inside it, 56.. time inside the fused issue + probe steps.
 #ifdef XVEC_DEBUG
 #define XVEC_SDBG(p, bit) ((p).dbg & (bit))
 #define XVEC_CNT(...) __VA_ARGS__
@@ -173,45 +175,60 @@ struct MmaRing {
   RingPos<kSlots> pos;  // the next slot to pop
   uint32_t rdy = 0;     // bit0 next slab seen full, bit1 next weight tile seen full
 };
+// The per-layer constants of the K loop, read ONCE per tile into registers: every inline-asm step carries a "memory" clobber,
+// so fields of the __grid_constant__ parameter block would otherwise be re-read (indexed constant loads, ~30-60 cycles each,
+// on the single-warp critical path) in every K step.  Tap offsets (<= 8) are packed four bits each.
+struct TileK {
+  int cpt, taps;
+  uint32_t tap_off4;
+  __device__ __forceinline__ explicit TileK(const StackLayer& L) : cpt(L.cpt), taps(L.taps), tap_off4(0) {
+    for (int j = 0; j < L.taps; ++j) tap_off4 |= static_cast<uint32_t>(L.tap_off[j]) << (4 * j);
+  }
+};
+static_assert(XVEC_MAX_TAPS <= 8 && XVEC_STACK_MAX_TAP_OFFSET < 16, "tap offsets are packed into 8 x 4 bits");
+
 template <bool kTf32, int kSlots>
-__device__ __forceinline__ void mma_tile(uint8_t* base, uint64_t* full, uint64_t* empty, uint32_t d, const StackLayer& L, MmaRing<kSlots>& r,
+__device__ __forceinline__ void mma_tile(uint32_t ring_addr, uint32_t full_addr, uint32_t empty_addr, uint32_t d, const TileK k, MmaRing<kSlots>& r,
                                          bool swap_ab, unsigned long long& c_wait, unsigned long long& c_step) {
   constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
+  const uint64_t desc0 = umma_desc_sw128(ring_addr);  // descriptor of slot 0, row 0
   uint32_t acc = 0;
-  for (int ch = 0; ch < L.cpt; ++ch) {
+  for (int ch = 0; ch < k.cpt; ++ch) {
     if (!(r.rdy & 1u)) {
       XVEC_CNT(const long long t0 = clock64();)
-      mbar_wait(&full[r.pos.slot], r.pos.ph, 3);
+      mbar_wait_a(full_addr + 8u * r.pos.slot, r.pos.ph, 3);
       XVEC_CNT(c_wait += clock64() - t0;)
     }
     r.rdy &= ~1u;  // bit0 is set again by the last tap's probe of the NEXT slab
     const int a_slot = r.pos.slot;
     r.pos = r.pos.next();
-    const uint32_t slab_addr = smem_u32(base + a_slot * SLOT_BYTES);
-    for (int tap = 0; tap < L.taps; ++tap) {
+    // operand descriptors are linear in the slot index and the tap's row shift (start address >> 4 in the low 14 bits; shared
+    // memory ends below 256 KiB, so nothing carries out of the field): one multiply-add per operand instead of mask / shift / or
+    const uint64_t slab_desc = desc0 + static_cast<uint32_t>(a_slot * (SLOT_BYTES >> 4));
+    for (int tap = 0; tap < k.taps; ++tap) {
       if (!(r.rdy & 2u)) {
         XVEC_CNT(const long long t0 = clock64();)
-        mbar_wait(&full[r.pos.slot], r.pos.ph, 3);
+        mbar_wait_a(full_addr + 8u * r.pos.slot, r.pos.ph, 3);
         XVEC_CNT(c_wait += clock64() - t0;)
       }
       tc_fence_after();
       const int b_slot = r.pos.slot;
       r.pos = r.pos.next();
-      const uint32_t x_addr = slab_addr + static_cast<uint32_t>(L.tap_off[tap]) * BK_BYTES;  // the slab, shifted by the tap's rows
-      const uint32_t w_addr = smem_u32(base + b_slot * SLOT_BYTES);
+      const uint64_t x_desc = slab_desc + ((k.tap_off4 >> (4 * tap)) & 15u) * (BK_BYTES >> 4);  // the slab, shifted by the tap's rows
+      const uint64_t w_desc = desc0 + static_cast<uint32_t>(b_slot * (SLOT_BYTES >> 4));
       // swap_ab: the weights are the M operand and the frames the N operand, i.e. the accumulator holds the TRANSPOSED tile
       // (TMEM lane = channel, column = frame).  Both operands are 128 rows x 128 bytes K-major, so it is only a swap.
-      const uint64_t da = umma_desc_sw128(swap_ab ? w_addr : x_addr);
-      const uint64_t db = umma_desc_sw128(swap_ab ? x_addr : w_addr);
+      const uint64_t da = swap_ab ? w_desc : x_desc;
+      const uint64_t db = swap_ab ? x_desc : w_desc;
       // what the next step pops: after the last tap the next chunk's slab (also across a tile boundary) and then its first
       // weight tile, otherwise the next tap's weight tile
-      const bool last_tap = tap == L.taps - 1;
+      const bool last_tap = tap == k.taps - 1;
       const RingPos<kSlots> pa = r.pos;
       const RingPos<kSlots> pb = last_tap ? r.pos.next() : r.pos;
       const uint32_t flags = STEP_COMMIT_B | STEP_PROBE_B | (last_tap ? (STEP_COMMIT_A | STEP_PROBE_A) : 0u);
       XVEC_CNT(const long long ts = clock64();)
-      const uint32_t got = umma_step_pair<kTf32>(elect_one() ? 1u : 0u, d, da, db, idesc, acc, flags, smem_u32(&empty[a_slot]),
-                                                 smem_u32(&empty[b_slot]), smem_u32(&full[pa.slot]), pa.ph, smem_u32(&full[pb.slot]), pb.ph);
+      const uint32_t got = umma_step_pair<kTf32>(elect_one() ? 1u : 0u, d, da, db, idesc, acc, flags, empty_addr + 8u * a_slot,
+                                                 empty_addr + 8u * b_slot, full_addr + 8u * pa.slot, pa.ph, full_addr + 8u * pb.slot, pb.ph);
       XVEC_CNT(c_step += clock64() - ts;)
       r.rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
       acc = 1u;
@@ -273,6 +290,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // shared-memory addresses the hot loops index by slot (see mbar_wait_a): the ring, its barriers, the leader's full barriers
+  const uint32_t ring_addr = smem_u32(base), full_addr = smem_u32(full_bar), empty_addr = smem_u32(empty_bar);
+  const uint32_t full_leader = mapa_u32(full_addr, 0);
   XVEC_CNT(long long dbg_c0 = clock64(); unsigned long long dbg_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));)
 
   // Consumer side of the work-item ring: wait for entry `it`, read it, hand the slot back to the scheduler.
@@ -304,36 +324,41 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       if (rank == 0 && lane == 0) mbar_arrive(&credit_bar[it % CREDIT_BARS]);  // tile `it` has started: the scheduler may draw item it + run-ahead
       const int layer = item & 7u, nt = (item >> 3) & 31u, mt = item >> 8;
       const StackLayer& L = p.L[layer];
+      // everything the K loop needs from the parameter block, in registers (the asm steps clobber "memory": see TileK)
+      const int cpt = L.cpt, taps = L.taps, n_pad = L.n_pad;
       const int bke = (kAllTf32 || L.tf32) ? 32 : 64;  // elements per 128-byte chunk
       const int m0 = mt * BM + static_cast<int>(rank) * BM_CTA;
       const int n0 = nt * BN + static_cast<int>(rank) * BN_CTA;
       const CUtensorMap* ma = &maps.a[layer];
       const CUtensorMap* mb = &maps.b[layer];
       const uint32_t slab_tx = 2u * static_cast<uint32_t>(L.slab_rows) * BK_BYTES;  // bytes of both CTAs' slabs
-      // timing experiment (debug bit 32): no activation loads for n-tiles > 0 of single-tap layers, as if the m-tile's activation
-      // chunks were resident in shared memory (the MMAs then read stale slabs: wrong results, right timing)
-      const bool skip_a = XVEC_SDBG(p, 32) && L.taps == 1 && nt > 0;
-      for (int ch = 0; ch < L.cpt; ++ch) {
-        if (!(rdy & 1u)) mbar_wait(&empty_bar[pos.slot], pos.ph ^ 1u, 1);
+      const unsigned long long pol_a = p.pol_a, pol_b = p.pol_b;
+      const uint32_t is_leader = rank == 0 ? 1u : 0u;
+      // timing experiments (debug bits 32 / 128): no activation / weight loads for n-tiles > 0 of single-tap layers, as if they
+      // were resident in shared memory (the MMAs then read stale slots: wrong results, right timing)
+      const bool skip_a = XVEC_SDBG(p, 32) && taps == 1 && nt > 0;
+      const bool skip_b = XVEC_SDBG(p, 128) && taps == 1 && nt > 0;
+      for (int ch = 0; ch < cpt; ++ch) {
+        if (!(rdy & 1u)) mbar_wait_a(empty_addr + 8u * pos.slot, pos.ph ^ 1u, 1);
         rdy &= ~1u;
         const int a_slot = pos.slot;
         pos = pos.next();
-        for (int tap = 0; tap < L.taps; ++tap) {
-          if (!(rdy & 2u)) mbar_wait(&empty_bar[pos.slot], pos.ph ^ 1u, 1);
+        int b_row = ch * n_pad + n0;  // row of the (tap, chunk) weight tile in the chunk-major packed matrix: (tap * cpt + ch) * n_pad + n0
+        for (int tap = 0; tap < taps; ++tap, b_row += cpt * n_pad) {
+          if (!(rdy & 2u)) mbar_wait_a(empty_addr + 8u * pos.slot, pos.ph ^ 1u, 1);
           const int b_slot = pos.slot;
           pos = pos.next();
           // the slots the next step fills: after the last tap the next chunk's slab (also across a tile boundary) and its
           // first weight tile, otherwise the next tap's weight tile
-          const bool last_tap = tap == L.taps - 1;
+          const bool last_tap = tap == taps - 1;
           const RingPos<RING_SLOTS> pa = pos;
           const RingPos<RING_SLOTS> pb = last_tap ? pos.next() : pos;
-          if (skip_a && tap == 0 && rank == 0 && elect_one()) mbar_expect_tx(&full_bar[a_slot], 0);  // completes the phase with no bytes
+          if (skip_a && tap == 0 && rank == 0 && elect_one()) mbar_expect_tx_a(full_addr + 8u * a_slot, 0);  // completes the phase with no bytes
           const uint32_t got = tma_step_slab(
-              elect_one() ? 1u : 0u, rank == 0 ? 1u : 0u, (tap == 0 && !skip_a) ? 1u : 0u, smem_u32(&full_bar[a_slot]),
-              mapa_u32(smem_u32(&full_bar[a_slot]), 0), slab_tx, smem_u32(base + a_slot * SLOT_BYTES), ma, ch * bke, m0, p.pol_a,
-              smem_u32(&full_bar[b_slot]), mapa_u32(smem_u32(&full_bar[b_slot]), 0), 2u * B_BYTES, smem_u32(base + b_slot * SLOT_BYTES), mb,
-              0, (tap * L.cpt + ch) * L.n_pad + n0, p.pol_b, smem_u32(&empty_bar[pb.slot]), pb.ph ^ 1u, last_tap ? 1u : 0u,
-              smem_u32(&empty_bar[pa.slot]), pa.ph ^ 1u);
+              elect_one() ? 1u : 0u, is_leader, (tap == 0 && !skip_a) ? 1u : 0u, full_addr + 8u * a_slot, full_leader + 8u * a_slot, slab_tx,
+              ring_addr + a_slot * SLOT_BYTES, ma, ch * bke, m0, pol_a, full_addr + 8u * b_slot, full_leader + 8u * b_slot,
+              skip_b ? 0u : 2u * B_BYTES, ring_addr + b_slot * SLOT_BYTES, mb, 0, b_row, pol_b, empty_addr + 8u * pb.slot, pb.ph ^ 1u,
+              last_tap ? 1u : 0u, empty_addr + 8u * pa.slot, pa.ph ^ 1u, skip_b ? 0u : 1u);
           rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
         }
       }
@@ -352,6 +377,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         const uint32_t item = ring_read(it);
         XVEC_CNT(c_ring += clock64() - tr;)
         if (item == ITEM_DONE) break;
+        XVEC_CNT(if (lane == 0) atomicAdd(p.counter + 32 + (item & 7u), static_cast<unsigned>((clock64() - tr) >> 4));)  // work-item wait per layer
         const StackLayer& L = p.L[item & 7u];
         const int buf = it & 1;
         const uint32_t use = (it >> 1) & 1;
@@ -360,8 +386,15 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         XVEC_CNT(c_tempty += clock64() - t0; const int dl = item & 7u; if (lane == 0) atomicAdd(p.counter + 16 + dl, static_cast<unsigned>((clock64() - t0) >> 4));)
         const uint32_t d = tmem_base + buf * BN;
         const bool pooled = static_cast<int>(item & 7u) == p.n_layers - 1;  // last layer: transposed accumulator (see the epilogue)
-        if (kAllTf32 || L.tf32) mma_tile<true>(base, full_bar, empty_bar, d, L, ring, pooled, c_full, c_step);
-        else mma_tile<false>(base, full_bar, empty_bar, d, L, ring, pooled, c_full, c_step);
+        XVEC_CNT(const long long tk = clock64(); const unsigned long long full0 = c_full, step0 = c_step;)
+        const TileK tk_(L);
+        if (kAllTf32 || L.tf32) mma_tile<true>(ring_addr, full_addr, empty_addr, d, tk_, ring, pooled, c_full, c_step);
+        else mma_tile<false>(ring_addr, full_addr, empty_addr, d, tk_, ring, pooled, c_full, c_step);
+        XVEC_CNT(if (lane == 0) {  // per layer: whole K loop, explicit operand waits, time inside the fused issue + probe step
+          atomicAdd(p.counter + 40 + (item & 7u), static_cast<unsigned>((clock64() - tk) >> 4));
+          atomicAdd(p.counter + 48 + (item & 7u), static_cast<unsigned>((c_full - full0) >> 4));
+          atomicAdd(p.counter + 56 + (item & 7u), static_cast<unsigned>((c_step - step0) >> 4));
+        })
         if (elect_one()) umma_commit_pair(&tfull_bar[buf], 0x3);  // accumulator complete (both CTAs' epilogues)
         __syncwarp();
         XVEC_CNT(if (lane == 0) atomicAdd(p.counter + 24 + (item & 7u), static_cast<unsigned>((clock64() - tr) >> 4));)
@@ -682,7 +715,7 @@ int64_t stack_plan(int64_t rows, int n_layers, const int32_t* n_tiles_per_layer,
 int64_t stack_ctrl_bytes(int64_t rows, int n_layers) {
   if (rows <= 0 || n_layers < 2) return 0;
   const int64_t m_tiles = (rows + BM - 1) / BM;
-  return 128 + (n_layers - 1) * m_tiles * 4 + n_layers * m_tiles * 4;  // counters | ready[layers - 1][m_tiles] | consumed[layers][m_tiles]
+  return 256 + (n_layers - 1) * m_tiles * 4 + n_layers * m_tiles * 4;  // counters (64 words) | ready[layers - 1][m_tiles] | consumed[layers][m_tiles]
 }
 
 XVEC_DEFINE_WATCHDOG_BINDER(bind_watchdog_stack)
@@ -899,7 +932,7 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
     all_tf32 = hit->all_tf32;
   }
   p.counter = static_cast<unsigned*>(ctrl);
-  p.ready = reinterpret_cast<unsigned*>(static_cast<char*>(ctrl) + 128);
+  p.ready = reinterpret_cast<unsigned*>(static_cast<char*>(ctrl) + 256);
   p.consumed = p.ready + static_cast<size_t>(n_tdnn - 1) * p.m_tiles;
   p.act[0] = static_cast<char*>(act0);
   p.act[1] = static_cast<char*>(act1);

@@ -55,7 +55,7 @@ for band in args.band.split(","):
     for dbg in args.dbg.split(","):
         os.environ["XVEC_STACK_DBG"] = dbg
         avg, best = run(args.iters, int(band))
-        cnt = sc.ctrl[:128].view(torch.int32).tolist()
+        cnt = sc.ctrl[:256].view(torch.int32).tolist()
         extra = ("  counters(spun,polls,fw,pub,mma_full,mma_tempty)=" + str([c for c in cnt[1:7]])) if any(cnt[1:7]) else ""
         if cnt[9]:
             extra += f" sm_clock={cnt[8] * 64 / cnt[9]:.3f} GHz cta0={cnt[9] / 1e3:.1f} us cta0_cycles={cnt[8] * 64} mma_step_cycles/pair={cnt[10] * 64 // 74} mma_ring_wait/pair={cnt[11] * 64 // 74} mma_full/pair={cnt[5] * 64 // 74} mma_tempty/pair={cnt[6] * 64 // 74}"
@@ -64,4 +64,6 @@ for band in args.band.split(","):
             ideal = [2560, 12288, 12288, 4096, 4096]
             extra += " per-layer cycles/tile (total incl. waits, tempty wait, ideal MMA): " + ", ".join(
                 f"L{l + 1}: {cnt[24 + l] * 16 // tiles[l]} / {cnt[16 + l] * 16 // tiles[l]} / {ideal[l]}" for l in range(5))
+            extra += " | item wait, K loop, operand waits, in-step: " + ", ".join(
+                f"L{l + 1}: {cnt[32 + l] * 16 // tiles[l]} {cnt[40 + l] * 16 // tiles[l]} {cnt[48 + l] * 16 // tiles[l]} {cnt[56 + l] * 16 // tiles[l]}" for l in range(5))
         print(f"band={band:>5} dbg={dbg}{extra} avg {avg * 1e3:8.1f} us  best {best * 1e3:8.1f} us  {flops / avg / 1e9:7.1f} TFLOP/s", flush=True)
