@@ -388,6 +388,32 @@ __device__ __forceinline__ uint32_t tma_step_slab(uint32_t elected, uint32_t is_
   return rdy;
 }
 
+// One producer step for ONE operand (tdnn_stack.cu runs the activation slabs and the weight tiles on two producer warps): every
+// lane probes (test_wait, non-blocking) the empty barrier of the slot this warp fills NEXT, then the elected lane arms the
+// leader's full barrier (leader only; the bytes of both CTAs) and issues this CTA's tensor load.  Returns 1 if the next slot
+// was seen free.  do_load = 0 arms / loads nothing (timing experiments).
+__device__ __forceinline__ uint32_t tma_step_one(uint32_t elected, uint32_t is_leader, uint32_t do_load, uint32_t bar_local, uint32_t bar_leader,
+                                                 uint32_t tx, uint32_t smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t pol,
+                                                 uint32_t probe_bar, uint32_t probe_par) {
+  uint32_t rdy;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pl, pw;\n\t"
+      "setp.ne.b32 pe, %1, 0;\n\t"
+      "setp.ne.b32 pl, %2, 0;\n\t"
+      "and.pred pl, pl, pe;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pw, [%11], %12;\n\t"
+      "@pl mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %5;\n\t"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%6], [%7, {%8, %9}], [%4], %10;\n\t"
+      "selp.u32 %0, 1, 0, pw;\n\t"
+      "}"
+      : "=r"(rdy)
+      : "r"(elected & do_load), "r"(is_leader), "r"(bar_local), "r"(bar_leader), "r"(tx), "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)),
+        "r"(c0), "r"(c1), "l"(pol), "r"(probe_bar), "r"(probe_par)
+      : "memory");
+  return rdy;
+}
+
 enum { STEP_COMMIT_A = 1, STEP_COMMIT_B = 2, STEP_PROBE_A = 4, STEP_PROBE_B = 8 };
 template <bool kTf32>
 __device__ __forceinline__ uint32_t umma_step_pair(uint32_t elected, uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,

@@ -76,9 +76,10 @@ constexpr int SCHED_SLOTS = 8;            // work-item ring between the schedule
 constexpr int CREDIT_BARS = 4;            // "tile started" barriers; the scheduler's run-ahead must stay below this (see the scheduler warp)
 constexpr int STACK_RUNAHEAD = 1;         // items a pair may hold that its producer has not started (p.runahead); measured: 1, 2, 3 give the same launch time
 constexpr uint32_t ITEM_DONE = 0xFFFFFFFFu;
-constexpr int SCHED_CONSUMERS = 2 * EPI_WARPS + 4;  // per slot: both producers, leader MMA warp, peer dependency warp, 8 epilogue warps of each CTA
+constexpr int SCHED_CONSUMERS = 2 * EPI_WARPS + 6;  // per slot: the two producer warps of both CTAs, leader MMA warp, peer dependency warp, 8 epilogue warps of each CTA
 constexpr int DEP_WARP = 2 + EPI_WARPS;             // warp 10
-constexpr int STACK_THREADS = GEMM_THREADS + 32;
+constexpr int WPROD_WARP = DEP_WARP + 1;            // warp 11: the weight-tile producer (warp 0 loads the activation slabs)
+constexpr int STACK_THREADS = GEMM_THREADS + 64;
 
 struct StackLayer {
   int n, n_tiles, taps, cpt;  // K loop = taps * cpt chunks of 128 bytes
@@ -163,6 +164,12 @@ struct RingPos {
   __device__ __forceinline__ RingPos next() const {
     RingPos n = *this;
     if (++n.slot == kSlots) { n.slot = 0; n.ph ^= 1u; }
+    return n;
+  }
+  __device__ __forceinline__ RingPos skip(int k) const {  // k <= kSlots positions further
+    RingPos n = *this;
+    n.slot += k;
+    if (n.slot >= kSlots) { n.slot -= kSlots; n.ph ^= 1u; }
     return n;
   }
 };
@@ -307,63 +314,73 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     return item;
   };
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    // Per tile: read the work item (published by the scheduler warp while the previous tile was loading), check that this
-    // CTA's dependency warp has resolved its inputs, tell the scheduler that the tile has started, then run the K loop.
-    RingPos<RING_SLOTS> pos;  // the next slot to fill
-    uint32_t rdy = 0;  // bit0 the slot of the next slab seen free, bit1 the slot of the next weight tile seen free
+  if (warp == 0 || warp == WPROD_WARP) {
+    // ------------------------------------------------------------------ TMA producers (both CTAs): warp 0 loads the activation
+    // slabs, warp WPROD_WARP the weight tiles.  Round 2: once the MMA warp's instruction stream was out of the way, ONE producer
+    // warp issuing both operands (~120 instructions and two TMA issues per K step) could not keep the ring full — the MMA warp
+    // waited ~2 500 cycles per TDNN2/3 tile for operands.  Both warps walk the same ring positions (per chunk: slab, then one
+    // weight tile per tap) and each fills its own; they never talk to each other.
+    // Per tile: read the work item (published by the scheduler warp while the previous tile was loading); the slab warp checks
+    // that this CTA's dependency warp has resolved the tile's inputs (weights have no dependencies) and tells the scheduler that
+    // the tile has started; then the K loop.
+    const bool slabs = warp == 0;
+    static_assert(XVEC_MAX_TAPS + 1 <= StackCfg<kAllTf32>::SLOTS, "RingPos::skip wraps at most once");
+    RingPos<RING_SLOTS> pos;  // ring position of the current chunk's slab
+    uint32_t rdy = 0;         // the slot this warp fills next was seen free
     XVEC_CNT(unsigned long long c_fw = 0, c_pub = 0;)
     for (int it = 0;; ++it) {
       XVEC_CNT(long long t0 = clock64();)
       const uint32_t item = ring_read(it);
       XVEC_CNT(c_pub += clock64() - t0; t0 = clock64();)
       if (item == ITEM_DONE) break;
-      mbar_wait(&dep_bar[it % SCHED_SLOTS], (it / SCHED_SLOTS) & 1u, 7);
-      XVEC_CNT(c_fw += clock64() - t0;)
-      if (rank == 0 && lane == 0) mbar_arrive(&credit_bar[it % CREDIT_BARS]);  // tile `it` has started: the scheduler may draw item it + run-ahead
+      if (slabs) {
+        mbar_wait(&dep_bar[it % SCHED_SLOTS], (it / SCHED_SLOTS) & 1u, 7);
+        XVEC_CNT(c_fw += clock64() - t0;)
+        if (rank == 0 && lane == 0) mbar_arrive(&credit_bar[it % CREDIT_BARS]);  // tile `it` has started: the scheduler may draw item it + run-ahead
+      }
       const int layer = item & 7u, nt = (item >> 3) & 31u, mt = item >> 8;
       const StackLayer& L = p.L[layer];
       // everything the K loop needs from the parameter block, in registers (the asm steps clobber "memory": see TileK)
       const int cpt = L.cpt, taps = L.taps, n_pad = L.n_pad;
-      const int bke = (kAllTf32 || L.tf32) ? 32 : 64;  // elements per 128-byte chunk
-      const int m0 = mt * BM + static_cast<int>(rank) * BM_CTA;
-      const int n0 = nt * BN + static_cast<int>(rank) * BN_CTA;
-      const CUtensorMap* ma = &maps.a[layer];
-      const CUtensorMap* mb = &maps.b[layer];
-      const uint32_t slab_tx = 2u * static_cast<uint32_t>(L.slab_rows) * BK_BYTES;  // bytes of both CTAs' slabs
-      const unsigned long long pol_a = p.pol_a, pol_b = p.pol_b;
       const uint32_t is_leader = rank == 0 ? 1u : 0u;
-      // timing experiments (debug bits 32 / 128): no activation / weight loads for n-tiles > 0 of single-tap layers, as if they
-      // were resident in shared memory (the MMAs then read stale slots: wrong results, right timing)
-      const bool skip_a = XVEC_SDBG(p, 32) && taps == 1 && nt > 0;
-      const bool skip_b = XVEC_SDBG(p, 128) && taps == 1 && nt > 0;
-      for (int ch = 0; ch < cpt; ++ch) {
-        if (!(rdy & 1u)) mbar_wait_a(empty_addr + 8u * pos.slot, pos.ph ^ 1u, 1);
-        rdy &= ~1u;
-        const int a_slot = pos.slot;
-        pos = pos.next();
-        int b_row = ch * n_pad + n0;  // row of the (tap, chunk) weight tile in the chunk-major packed matrix: (tap * cpt + ch) * n_pad + n0
-        for (int tap = 0; tap < taps; ++tap, b_row += cpt * n_pad) {
-          if (!(rdy & 2u)) mbar_wait_a(empty_addr + 8u * pos.slot, pos.ph ^ 1u, 1);
-          const int b_slot = pos.slot;
-          pos = pos.next();
-          // the slots the next step fills: after the last tap the next chunk's slab (also across a tile boundary) and its
-          // first weight tile, otherwise the next tap's weight tile
-          const bool last_tap = tap == taps - 1;
-          const RingPos<RING_SLOTS> pa = pos;
-          const RingPos<RING_SLOTS> pb = last_tap ? pos.next() : pos;
-          if (skip_a && tap == 0 && rank == 0 && elect_one()) mbar_expect_tx_a(full_addr + 8u * a_slot, 0);  // completes the phase with no bytes
-          const uint32_t got = tma_step_slab(
-              elect_one() ? 1u : 0u, is_leader, (tap == 0 && !skip_a) ? 1u : 0u, full_addr + 8u * a_slot, full_leader + 8u * a_slot, slab_tx,
-              ring_addr + a_slot * SLOT_BYTES, ma, ch * bke, m0, pol_a, full_addr + 8u * b_slot, full_leader + 8u * b_slot,
-              skip_b ? 0u : 2u * B_BYTES, ring_addr + b_slot * SLOT_BYTES, mb, 0, b_row, pol_b, empty_addr + 8u * pb.slot, pb.ph ^ 1u,
-              last_tap ? 1u : 0u, empty_addr + 8u * pa.slot, pa.ph ^ 1u, skip_b ? 0u : 1u);
-          rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
+      if (slabs) {
+        const int bke = (kAllTf32 || L.tf32) ? 32 : 64;  // elements per 128-byte chunk
+        const int m0 = mt * BM + static_cast<int>(rank) * BM_CTA;
+        const CUtensorMap* ma = &maps.a[layer];
+        const uint32_t slab_tx = 2u * static_cast<uint32_t>(L.slab_rows) * BK_BYTES;  // bytes of both CTAs' slabs
+        const unsigned long long pol_a = p.pol_a;
+        // timing experiment (debug bit 32): no activation loads for n-tiles > 0 of single-tap layers, as if the m-tile's
+        // activation chunks were resident in shared memory (the MMAs then read stale slots: wrong results, right timing)
+        const bool skip_a = XVEC_SDBG(p, 32) && taps == 1 && nt > 0;
+        for (int ch = 0; ch < cpt; ++ch) {
+          if (!rdy) mbar_wait_a(empty_addr + 8u * pos.slot, pos.ph ^ 1u, 1);
+          const RingPos<RING_SLOTS> nxt = pos.skip(1 + taps);  // the next chunk's slab, also across a tile boundary
+          if (skip_a && rank == 0 && elect_one()) mbar_expect_tx_a(full_addr + 8u * pos.slot, 0);  // completes the phase with no bytes
+          rdy = tma_step_one(elect_one() ? 1u : 0u, is_leader, skip_a ? 0u : 1u, full_addr + 8u * pos.slot, full_leader + 8u * pos.slot, slab_tx,
+                             ring_addr + pos.slot * SLOT_BYTES, ma, ch * bke, m0, pol_a, empty_addr + 8u * nxt.slot, nxt.ph ^ 1u);
+          pos = nxt;
+        }
+      } else {
+        const int n0 = nt * BN + static_cast<int>(rank) * BN_CTA;
+        const CUtensorMap* mb = &maps.b[layer];
+        const unsigned long long pol_b = p.pol_b;
+        const bool skip_b = XVEC_SDBG(p, 128) && taps == 1 && nt > 0;  // (debug bit 128) the same for the weight tiles
+        for (int ch = 0; ch < cpt; ++ch) {
+          RingPos<RING_SLOTS> pb = pos.next();  // the chunk's first weight tile sits behind its slab
+          int b_row = ch * n_pad + n0;          // row of the (tap, chunk) tile in the chunk-major packed matrix: (tap * cpt + ch) * n_pad + n0
+          for (int tap = 0; tap < taps; ++tap, b_row += cpt * n_pad) {
+            if (!rdy) mbar_wait_a(empty_addr + 8u * pb.slot, pb.ph ^ 1u, 1);
+            const RingPos<RING_SLOTS> nxt = tap == taps - 1 ? pb.skip(2) : pb.next();  // after the last tap: over the next chunk's slab
+            if (skip_b && rank == 0 && elect_one()) mbar_expect_tx_a(full_addr + 8u * pb.slot, 0);
+            rdy = tma_step_one(elect_one() ? 1u : 0u, is_leader, skip_b ? 0u : 1u, full_addr + 8u * pb.slot, full_leader + 8u * pb.slot, 2u * B_BYTES,
+                               ring_addr + pb.slot * SLOT_BYTES, mb, 0, b_row, pol_b, empty_addr + 8u * nxt.slot, nxt.ph ^ 1u);
+            pb = nxt;
+          }
+          pos = pos.skip(1 + taps);
         }
       }
     }
-    XVEC_CNT(if (lane == 0) {
+    XVEC_CNT(if (slabs && lane == 0) {
       atomicAdd(p.counter + 3, static_cast<unsigned>(c_fw >> 6));
       atomicAdd(p.counter + 4, static_cast<unsigned>(c_pub >> 6));
     })
