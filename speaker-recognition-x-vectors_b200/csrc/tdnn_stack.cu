@@ -20,6 +20,10 @@
 //     The two ping-pong activation buffers are safe: tile (l, m) overwrites rows whose readers (l-1, m-1) and (l-1, m) it
 //     has just waited for.
 //
+//   * warp roles (384 threads): 0 activation-slab producer, 1 MMA issuer (leader CTA), 2-9 epilogue, 10 scheduler (leader) +
+//     dependency resolver, 11 weight-tile producer.  What paces the tensor pipe is the instruction stream of the ONE MMA warp
+//     (512 cycles of tensor work per K step): its loop keeps everything in registers and probes barriers without blocking.
+//
 // TMEM double buffering and the tcgen05 step are the ones of tdnn_gemm.cu.  Layers 1.. run kind::f16 (bf16) or kind::tf32
 // (kAllTf32); layer 0 runs in its own dtype: kind::tf32 on the float32 MFCCs, or kind::f16 on a bf16 copy of them in "window
 // form" (taps = 1, cin = taps*channels over overlapping rows; include/xvec_b200.h).  The last layer is computed TRANSPOSED
