@@ -31,8 +31,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
-
 // One lane of a fully converged warp (warp-uniform control flow keeps addresses/descriptors in uniform registers; only the
 // single-thread instructions — TMA, tcgen05.mma, tcgen05.commit — are predicated on the elected lane).
 __device__ __forceinline__ bool elect_one() {
@@ -163,12 +161,6 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -194,27 +186,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-// 2-D tiled load global -> shared, completion bytes signalled on `bar`. Out-of-bounds elements are zero-filled.
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// L2 prefetch of a tile (no shared-memory destination): turns a later TMA load of the same box into an L2 hit.
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
-}
-// CTA-pair variant: the data lands in this CTA's shared memory, the completion bytes are signalled on a barrier
-// given by its shared::cluster address (the leader CTA's barrier).
-__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0, int32_t c1,
-                                                 uint64_t l2_policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(l2_policy)
-      : "memory");
-}
 // 2-D tiled store shared -> global (bulk async group); rows / columns outside the tensor are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, uint64_t l2_policy) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
@@ -238,15 +209,6 @@ __device__ __forceinline__ void tma_store_wait_done() {
 }
 
 // ----------------------------------------------------------------------------- tensor memory
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp, the one that allocated
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
 // CTA-pair variants: the same warp index of BOTH CTAs of the pair issues them.
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {
@@ -271,39 +233,6 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t m, uint
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
-template <bool kTf32>
-__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (kTf32) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-// CTA-pair MMA (M = 256 over two SMs), issued by one thread of the leader CTA for both.
-template <bool kTf32>
-__device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (kTf32) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
 // One K step of the CTA-pair mainloop as a single instruction group, issued by a converged warp:
 //   - the elected lane issues the four tcgen05.mma of this 128-byte K chunk (32 bytes of K each) and the commits that
 //     release the operand stages,
@@ -339,51 +268,6 @@ __device__ __forceinline__ uint32_t tma_step_pair(uint32_t elected, uint32_t is_
       : "r"(elected), "r"(is_leader), "r"(full_bar_local), "r"(full_bar_leader), "r"(tx_bytes), "r"(smem_a),
         "l"(reinterpret_cast<uint64_t>(map_a)), "r"(a0), "r"(a1), "l"(pol_a), "r"(smem_b), "l"(reinterpret_cast<uint64_t>(map_b)),
         "r"(b0), "r"(b1), "r"(probe_bar), "r"(probe_par), "l"(pol_b)
-      : "memory");
-  return rdy;
-}
-
-// Producer step of the slab pipeline (tdnn_stack.cu) as one instruction group (converged warp): the elected lane arms the
-// leader's barriers and issues [the activation slab load of a new channel chunk, if do_a] + the weight-tile load of this
-// (chunk, tap); then the warp probes (try_wait, may suspend) the empty barrier of the next weight stage and, if probe_a, of
-// the next slab.  Returns bit0 = next slab seen free, bit1 = next weight stage seen free.  (Round 2: the probes are test_wait,
-// issued before the loads, for the reason given at umma_step_pair.)
-__device__ __forceinline__ uint32_t tma_step_slab(uint32_t elected, uint32_t is_leader, uint32_t do_a, uint32_t fa_local, uint32_t fa_leader,
-                                                  uint32_t a_tx, uint32_t smem_a, const CUtensorMap* map_a, int32_t a0, int32_t a1,
-                                                  uint64_t pol_a, uint32_t fb_local, uint32_t fb_leader, uint32_t b_tx, uint32_t smem_b,
-                                                  const CUtensorMap* map_b, int32_t b0, int32_t b1, uint64_t pol_b, uint32_t probe_b_bar,
-                                                  uint32_t probe_b_par, uint32_t probe_a, uint32_t probe_a_bar, uint32_t probe_a_par,
-                                                  uint32_t do_b = 1u) {
-  uint32_t rdy;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred pe, pl, pa, pla, ppa, pwa, pwb, pb;\n\t"
-      ".reg .b32 ra, rb;\n\t"
-      "setp.ne.b32 pe, %1, 0;\n\t"
-      "setp.ne.b32 pl, %2, 0;\n\t"
-      "and.pred pl, pl, pe;\n\t"
-      "setp.ne.b32 pa, %3, 0;\n\t"
-      "and.pred pla, pa, pl;\n\t"
-      "and.pred pa, pa, pe;\n\t"
-      "setp.ne.b32 pb, %25, 0;\n\t"
-      "and.pred pb, pb, pe;\n\t"
-      "setp.ne.b32 ppa, %22, 0;\n\t"
-      "setp.ne.b32 pwa, 0, 0;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 pwb, [%20], %21;\n\t"
-      "@ppa mbarrier.test_wait.parity.shared::cta.b64 pwa, [%23], %24;\n\t"
-      "@pla mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %6;\n\t"
-      "@pa cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%7], [%8, {%9, %10}], [%5], %11;\n\t"
-      "@pl mbarrier.arrive.expect_tx.shared::cta.b64 _, [%12], %14;\n\t"
-      "@pb cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%15], [%16, {%17, %18}], [%13], %19;\n\t"
-      "selp.u32 ra, 1, 0, pwa;\n\t"
-      "selp.u32 rb, 2, 0, pwb;\n\t"
-      "or.b32 %0, ra, rb;\n\t"
-      "}"
-      : "=r"(rdy)
-      : "r"(elected), "r"(is_leader), "r"(do_a), "r"(fa_local), "r"(fa_leader), "r"(a_tx), "r"(smem_a),
-        "l"(reinterpret_cast<uint64_t>(map_a)), "r"(a0), "r"(a1), "l"(pol_a), "r"(fb_local), "r"(fb_leader), "r"(b_tx), "r"(smem_b),
-        "l"(reinterpret_cast<uint64_t>(map_b)), "r"(b0), "r"(b1), "l"(pol_b), "r"(probe_b_bar), "r"(probe_b_par), "r"(probe_a),
-        "r"(probe_a_bar), "r"(probe_a_par), "r"(do_b)
       : "memory");
   return rdy;
 }
@@ -469,11 +353,6 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
-// All previously issued tcgen05.mma of this thread arrive on `bar` when they complete (implies fence::before_thread_sync).
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread i gets lane i, v[j] = column j).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
