@@ -57,18 +57,36 @@ struct PoolArgs {
 // tcol: TMEM address of (this warp's lane quarter, first of its 128 columns); ch: this thread's channel; f0: frame of column 0
 // (a multiple of 128); release(): called once, right after the warp's last tcgen05.ld of the tile has landed (NOT called when
 // none of the warp's channels exist — the caller then releases the buffer itself).
-template <class Release>
-__device__ __forceinline__ void pool_epilogue_tile_t(const PoolArgs& p, uint32_t tcol, int ch, int f0, int lane, Release&& release) {
-  if (ch - lane >= p.n) return;  // warp-uniform: none of the warp's 32 channels exist
-  const float bch = (ch < p.n && p.bias) ? __ldg(p.bias + ch) : 0.f;
-  const float2 b2 = make_float2(bch, bch);
+// What a pooling tile reads from global memory before it can start: this thread's bias, the utterance of its frame in each of
+// the four 32-frame blocks, the first partial slot of the 128-frame group.  pool_prefetch() issues these loads; calling it
+// BEFORE the wait for the accumulator puts their ~700 cycles of L2 latency behind that wait instead of in front of the first
+// tcgen05.ld (the epilogue warps' per-tile latency chain is what the MMA warp ends up waiting for).
+struct PoolPrefetch {
+  float bch;
   int my_u[4];
+  int slot;
+};
+__device__ __forceinline__ PoolPrefetch pool_prefetch(const PoolArgs& p, int ch, int f0, int lane) {
+  PoolPrefetch q;
+  q.bch = (ch < p.n && p.bias) ? __ldg(p.bias + ch) : 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {  // frame -> utterance of the four 32-frame blocks (lane = frame within the block)
     const int f = f0 + 32 * k + lane;
-    my_u[k] = f < p.rows ? __ldg(p.row_utt + f) : -1;
+    q.my_u[k] = f < p.rows ? __ldg(p.row_utt + f) : -1;
   }
-  int slot = __ldg(p.blk_slot_base + (f0 / XVEC_POOL_BLOCK));
+  q.slot = __ldg(p.blk_slot_base + (f0 / XVEC_POOL_BLOCK));
+  return q;
+}
+template <class Release>
+__device__ __forceinline__ void pool_epilogue_tile_t(const PoolArgs& p, const PoolPrefetch& pre, uint32_t tcol, int ch, int f0, int lane,
+                                                     Release&& release) {
+  if (ch - lane >= p.n) return;  // warp-uniform: none of the warp's 32 channels exist
+  const float bch = pre.bch;
+  const float2 b2 = make_float2(bch, bch);
+  int my_u[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) my_u[k] = pre.my_u[k];
+  int slot = pre.slot;
   float* const part_ch = p.part + ch;
   const size_t slot_stride = 2 * static_cast<size_t>(p.n);
   uint32_t va[32], vb[32];

@@ -253,8 +253,9 @@ tdnn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       if constexpr (kEpi == EPI_POOL) {
         const PoolArgs pa{p.rows, p.n, p.bias, p.row_utt, p.blk_slot_base, p.part};
-        pool_epilogue_tile_t(pa, tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + cbeg,
-                             n0 + static_cast<int>(rank) * BN_CTA + q * 32 + lane, (tt / p.n_tiles) * BM + cbeg, lane, release_tmem);
+        const int pch = n0 + static_cast<int>(rank) * BN_CTA + q * 32 + lane, pf0 = (tt / p.n_tiles) * BM + cbeg;
+        pool_epilogue_tile_t(pa, pool_prefetch(pa, pch, pf0, lane), tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + cbeg, pch,
+                             pf0, lane, release_tmem);
       } else {
         uint8_t* out_stage = epi_smem + (warp - 2) * (OUT_BUFS * OUT_BUF_BYTES);  // 32-row x 128-byte staging boxes
         constexpr int OUT_ES = kEpi == EPI_STORE_BF16 ? 2 : 4;

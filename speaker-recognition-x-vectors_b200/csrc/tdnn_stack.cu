@@ -518,14 +518,14 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       }
       pend = nullptr;
     };
+    // The epilogue warps' per-tile chain — read the work item (~500 cycles), wait for the accumulator, fetch the pooling
+    // bookkeeping from L2 (~700 cycles), then four dependent tcgen05.ld + math rounds — is what the MMA warp ends up waiting
+    // for once the mainloop is fast (round 2).  So the chain is software-pipelined: item `it` is in hand when iteration `it`
+    // starts (read during iteration it - 1), its global loads are issued first, then item it + 1 is read while they are in
+    // flight, and only then does the warp wait for the accumulator.
+    // Never sleep on future work with an unpublished tile: a consumer of that tile may be what the future work waits for.
+    uint32_t item = ring_read(0);
     for (int it = 0;; ++it) {
-      // Never sleep on future work with an unpublished tile: a consumer of that tile may be what the future work waits for.
-      {
-        const int slot = it % SCHED_SLOTS;
-        const uint32_t sph = (it / SCHED_SLOTS) & 1u;
-        if (pend && !mbar_test_wait(&sfull_bar[slot], sph)) flush();
-      }
-      const uint32_t item = ring_read(it);
       if (item == ITEM_DONE) break;
       const int layer = item & 7u, nt = (item >> 3) & 31u, mt = item >> 8;
       const StackLayer& L = p.L[layer];
@@ -533,6 +533,18 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       const int n0 = nt * BN;
       const int buf = it & 1;
       const uint32_t use = (it >> 1) & 1;
+      const bool pooled_tile = layer == p.n_layers - 1;
+      const PoolArgs pa{p.rows, L.n, L.bias, p.row_utt, p.blk_slot_base, p.part};
+      const int pch = n0 + static_cast<int>(rank) * BN_CTA + q * 32 + lane, pf0 = mt * BM + cbeg;
+      PoolPrefetch pre{};
+      if (pooled_tile) pre = pool_prefetch(pa, pch, pf0, lane);
+      uint32_t next_item;
+      {
+        const int nslot = (it + 1) % SCHED_SLOTS;
+        const uint32_t nph = ((it + 1) / SCHED_SLOTS) & 1u;
+        if (pend && !mbar_test_wait(&sfull_bar[nslot], nph)) flush();
+        next_item = ring_read(it + 1);
+      }
       if (pend && !mbar_test_wait(&tfull_bar[buf], use)) flush();
       mbar_wait(&tfull_bar[buf], use, 4);
       tc_fence_after();
@@ -577,12 +589,10 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         if (layer != p.n_layers - 1) pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
         continue;
       }
-      if (layer == p.n_layers - 1) {
+      if (pooled_tile) {
         // Last layer: statistics-pooling partials; nothing is stored and nobody waits for this tile.  The accumulator is
         // TRANSPOSED (the MMA warp swapped the operands): TMEM lane = output channel, column = frame (gemm_tile.cuh).
-        const PoolArgs pa{p.rows, L.n, L.bias, p.row_utt, p.blk_slot_base, p.part};
-        pool_epilogue_tile_t(pa, tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + cbeg,
-                             n0 + static_cast<int>(rank) * BN_CTA + q * 32 + lane, mt * BM + cbeg, lane, release_tmem);
+        pool_epilogue_tile_t(pa, pre, tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + cbeg, pch, pf0, lane, release_tmem);
         if (!released) release_tmem();
         if (pend) flush();  // its stores were issued a whole tile ago
       } else {
@@ -647,6 +657,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         }
         pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
       }
+      item = next_item;
     }
     if (pend) flush();
     if (lane == 0) tma_store_wait_all();
