@@ -46,11 +46,11 @@ WORKLOAD = "c2: 1024 x 3 s utterances (300 x 24 MFCC) per step and GPU as 4 batc
 NCU_TENSOR_PIPE = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 78.3, "file": "profiles/r02_stack_ncu_full_summary.txt",
                    "note": "ncu --set full capture of one tdnn_stack_kernel launch (cold, serialised, 278.3 us at 1.60 GHz); ~7 % of the issued "
                            "MMA work is padding (don't-care rows of the flat layout, N 1500 -> 1536, K 120 -> 128)"}
-NCU_TENSOR_PIPE_TF32 = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 74.6, "file": "profiles/r02_pool_tf32_ncu_full_summary.txt",
-                        "note": "ncu --set full capture of one tdnn_stack_kernel<tf32> launch (556.5 us)"}
+NCU_TENSOR_PIPE_TF32 = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 86.4, "file": "profiles/r02_pool_tf32_ncu_full_summary.txt",
+                        "note": "ncu --set full capture of one tdnn_stack_kernel<tf32> launch (497.3 us at 1.59 GHz)"}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tdnn_stack_kernel launch on this workload (ncu --set full; see profiles/README.md)
 STACK_DRAM_BYTES = {"bf16": 185791232,   # 17.1 MB read + 168.7 MB written (final contents of the activation buffers)
-                    "tf32": 695182576}   # 120.9 MB read + 574.3 MB written: float32 activations of a band do not fit in L2
+                    "tf32": 697913928}   # 113.2 MB read + 584.7 MB written: float32 activations of a band do not fit in L2
 STACK_DRAM_SOURCE = {"bf16": "profiles/r02_stack_ncu_full_summary.txt", "tf32": "profiles/r02_pool_tf32_ncu_full_summary.txt"}
 
 
