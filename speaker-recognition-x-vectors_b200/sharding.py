@@ -127,5 +127,6 @@ def extract_sharded_flat(hx, flat_host: torch.Tensor, lengths_shard, parts: Sequ
     if gather is None:
         dim = (hx.model.segment_layer7 if hx.model.x_vec_extract_layer == 7 else hx.model.segment_layer6).out_features
         gather = RowGather(parts, n_total, dim, hx.device)
-    hx.extract_flat(flat_host, lengths_shard, max_frames=max_frames, to_host=False, batch_sizes=batch_sizes, out_dev=gather.local_view)
+    if len(lengths_shard):  # a rank may own nothing (fewer batches than ranks): it still takes part in the collective
+        hx.extract_flat(flat_host, lengths_shard, max_frames=max_frames, to_host=False, batch_sizes=batch_sizes, out_dev=gather.local_view)
     return gather()
