@@ -30,6 +30,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.xvec_packed_k(3000, 1, xvec_b200._lib.BF16) == 3008 and lib.xvec_packed_n(1500) == 1536
 
 
+def test_ctypes_signatures_have_the_headers_arity():
+    """Every declared entry point takes as many arguments in the ctypes binding as in include/xvec_b200.h (a wrong count would
+    shift pointers silently: ctypes does not check)."""
+    header = open(os.path.join(ROOT, "include", "xvec_b200.h")).read()
+    decls = re.findall(r"XVEC_API\s+[\w\s\*]+?\b(xvec_\w+)\s*\(([^;]*?)\);", header, re.S)
+    assert len(decls) == len(xvec_b200._lib.EXPORTS)
+    for name, params in decls:
+        params = params.strip()
+        n = 0 if params in ("void", "") else len([q for q in params.split(",") if q.strip()])
+        assert n == len(xvec_b200._lib._SIGNATURES[name][1]), name
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_fails_loudly_without_gpu():
     lib = xvec_b200._lib.load()
