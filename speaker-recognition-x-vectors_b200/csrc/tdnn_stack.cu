@@ -587,6 +587,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         release_tmem();
         if (pend) flush();
         if (layer != p.n_layers - 1) pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
+        item = next_item;
         continue;
       }
       if (pooled_tile) {
