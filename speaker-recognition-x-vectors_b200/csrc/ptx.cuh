@@ -348,6 +348,67 @@ __device__ __forceinline__ uint32_t umma_step_pair(uint32_t elected, uint32_t tm
 #undef XVEC_STEP_BODY
   return rdy;
 }
+// The same K step with everything that is fixed per (layer shape, tap position) decided at COMPILE time (tdnn_stack.cu,
+// mma_tile_fixed): what is committed / probed (kLastTap: this is the last tap of a channel chunk — hand the slab slot back,
+// probe the next slab), so no flag tests or predicate logic at run time; one predicate (the elected lane) on all six issue
+// instructions; and the operand descriptors advance in their low 32-bit word only (start address >> 4 in bits [0,14): + 2 per
+// 32 bytes of K, which cannot carry out of the field below 256 KiB of shared memory), so the uniform datapath does 32-bit adds
+// instead of 64-bit add-with-carry pairs chained through a carry predicate.
+template <bool kTf32, bool kLastTap>
+__device__ __forceinline__ uint32_t umma_step_fixed(uint32_t elected, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                    uint32_t acc0, uint32_t commit_a_bar, uint32_t commit_b_bar, uint32_t probe_a_bar,
+                                                    uint32_t probe_a_par, uint32_t probe_b_bar, uint32_t probe_b_par) {
+  uint32_t rdy;
+#define XVEC_FIXED_BODY(KIND, PROBE_A, COMMIT_A)                                                                  \
+  asm volatile(                                                                                                   \
+      "{\n\t"                                                                                                     \
+      ".reg .pred pe, pacc, pt, pwa, pwb;\n\t"                                                                    \
+      ".reg .b64 a0, a1, a2, a3, b0, b1, b2, b3;\n\t"                                                             \
+      ".reg .b32 ra, rb, t;\n\t"                                                                                  \
+      ".reg .b16 mk;\n\t"                                                                                         \
+      "mov.b16 mk, 3;\n\t"                                                                                        \
+      "setp.ne.b32 pe, %13, 0;\n\t"                                                                               \
+      "setp.ne.b32 pacc, %6, 0;\n\t"                                                                              \
+      "setp.eq.b32 pt, 0, 0;\n\t"                                                                                 \
+      "setp.ne.b32 pwa, 0, 0;\n\t"                                                                                \
+      PROBE_A                                                                                                     \
+      "mbarrier.test_wait.parity.shared::cta.b64 pwb, [%11], %12;\n\t"                                            \
+      "mov.b64 a0, {%2, %4};\n\t"                                                                                 \
+      "mov.b64 b0, {%3, %4};\n\t"                                                                                 \
+      "add.u32 t, %2, 2;\n\tmov.b64 a1, {t, %4};\n\t"                                                            \
+      "add.u32 t, %3, 2;\n\tmov.b64 b1, {t, %4};\n\t"                                                            \
+      "add.u32 t, %2, 4;\n\tmov.b64 a2, {t, %4};\n\t"                                                            \
+      "add.u32 t, %3, 4;\n\tmov.b64 b2, {t, %4};\n\t"                                                            \
+      "add.u32 t, %2, 6;\n\tmov.b64 a3, {t, %4};\n\t"                                                            \
+      "add.u32 t, %3, 6;\n\tmov.b64 b3, {t, %4};\n\t"                                                            \
+      "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%1], a0, b0, %5, pacc;\n\t"                                   \
+      "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%1], a1, b1, %5, pt;\n\t"                                     \
+      "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%1], a2, b2, %5, pt;\n\t"                                     \
+      "@pe tcgen05.mma.cta_group::2.kind::" KIND " [%1], a3, b3, %5, pt;\n\t"                                     \
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], mk;\n\t" \
+      COMMIT_A                                                                                                    \
+      "selp.u32 ra, 1, 0, pwa;\n\t"                                                                               \
+      "selp.u32 rb, 2, 0, pwb;\n\t"                                                                               \
+      "or.b32 %0, ra, rb;\n\t"                                                                                    \
+      "}"                                                                                                         \
+      : "=r"(rdy)                                                                                                 \
+      : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc0), "r"(commit_a_bar), "r"(commit_b_bar),  \
+        "r"(probe_a_bar), "r"(probe_a_par), "r"(probe_b_bar), "r"(probe_b_par), "r"(elected)                      \
+      : "memory")
+#define XVEC_FIXED_PROBE_A "mbarrier.test_wait.parity.shared::cta.b64 pwa, [%9], %10;\n\t"
+#define XVEC_FIXED_COMMIT_A "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], mk;\n\t"
+  if constexpr (kTf32) {
+    if constexpr (kLastTap) XVEC_FIXED_BODY("tf32", XVEC_FIXED_PROBE_A, XVEC_FIXED_COMMIT_A);
+    else XVEC_FIXED_BODY("tf32", "", "");
+  } else {
+    if constexpr (kLastTap) XVEC_FIXED_BODY("f16", XVEC_FIXED_PROBE_A, XVEC_FIXED_COMMIT_A);
+    else XVEC_FIXED_BODY("f16", "", "");
+  }
+#undef XVEC_FIXED_BODY
+#undef XVEC_FIXED_PROBE_A
+#undef XVEC_FIXED_COMMIT_A
+  return rdy;
+}
 // Pair commit: arrives on the same-offset barrier of every CTA in `cta_mask` once the issued MMAs complete.
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"

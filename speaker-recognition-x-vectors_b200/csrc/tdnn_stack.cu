@@ -32,6 +32,7 @@
 #include <cuda_bf16.h>
 
 #include <mutex>
+#include <type_traits>
 
 namespace xvec {
 
@@ -59,6 +60,11 @@ namespace xvec {
 // stay free), otherwise they wait for a whole stack kernel to drain — measured in round 1: ~24 us of a 325 us step.  Measured
 // here (256 x 300, bf16, us per launch on one box): 12 slots / 1 box 290.5, 11 / 2 boxes 291.9, 11 / 1 box 292.2 — the last
 // slot buys less than the co-residency it would cost.
+// XVEC_MMA_FIXED = 1: the MMA warp runs the K loop specialised at compile time for the tap counts the x-vector stack has
+// (mma_tile_fixed); 0: the generic loop for every layer (mma_tile).  Same MMAs in the same order either way.
+#ifndef XVEC_MMA_FIXED
+#define XVEC_MMA_FIXED 1
+#endif
 #ifndef XVEC_RING_SLOTS_BF16
 #define XVEC_RING_SLOTS_BF16 11
 #define XVEC_RING_SLOTS_F32 10
@@ -91,6 +97,7 @@ struct StackLayer {
   int slab_rows;              // 128 + largest tap offset: frame rows one activation slab holds (= the A tensor map's box)
   int n_pad;                  // rows of one K chunk of the chunk-major packed weights (n_tiles * 256)
   int tap_off[XVEC_MAX_TAPS];
+  unsigned tap_off4;          // the same, four bits each (tap j in bits [4j, 4j+4)): one constant load per tile on the MMA warp
   const float* bias;
 };
 
@@ -149,7 +156,8 @@ __host__ __device__ inline uint32_t decode_item(const StackParams& p, unsigned i
 // Debug builds also accumulate counters in the spare words of the control block (read by tools/stack_bench.py; units of 64
 // cycles unless stated): 1 tiles whose dependency warp had to spin on a flag (count), 2 flag polls (count), 3 producer waiting
 // for its dependency warp, 4 producer waiting for the work item, 5 MMA warp waiting for operands (explicit waits only),
-// 6 MMA warp waiting for a free accumulator buffer, 8 / 9 lifetime of CTA 0 in cycles / nanoseconds (SM clock), 10 time inside
+// 6 MMA warp waiting for a free accumulator buffer, 12 / 13 (pooled tiles) and 14 / 15 (stored tiles) one epilogue warp per pair
+// waiting for the accumulator / busy until it hands the buffer back, 7 the same warp after the release (stores, partials), 8 / 9 lifetime of CTA 0 in cycles / nanoseconds (SM clock), 10 time inside
 // the tcgen05 step, 11 MMA warp waiting for the work item, per layer (units of 16): 16.. accumulator wait, 24.. whole tile, 32.. work-item
 // wait, 40.. K loop, 48.. explicit operand waits inside it, 56.. time inside the fused issue + probe steps.
 #ifdef XVEC_DEBUG
@@ -192,9 +200,7 @@ struct MmaRing {
 struct TileK {
   int cpt, taps;
   uint32_t tap_off4;
-  __device__ __forceinline__ explicit TileK(const StackLayer& L) : cpt(L.cpt), taps(L.taps), tap_off4(0) {
-    for (int j = 0; j < L.taps; ++j) tap_off4 |= static_cast<uint32_t>(L.tap_off[j]) << (4 * j);
-  }
+  __device__ __forceinline__ explicit TileK(const StackLayer& L) : cpt(L.cpt), taps(L.taps), tap_off4(L.tap_off4) {}
 };
 static_assert(XVEC_MAX_TAPS <= 8 && XVEC_STACK_MAX_TAP_OFFSET < 16, "tap offsets are packed into 8 x 4 bits");
 
@@ -243,6 +249,61 @@ __device__ __forceinline__ void mma_tile(uint32_t ring_addr, uint32_t full_addr,
       XVEC_CNT(c_step += clock64() - ts;)
       r.rdy = (got & 2u) | (last_tap ? (got & 1u) : 0u);
       acc = 1u;
+    }
+  }
+}
+
+// The K loop for the tap counts the x-vector stack has (1: TDNN1 in window form, TDNN4, TDNN5; 3: TDNN2, TDNN3): the tap loop is
+// straight-line code with compile-time commit / probe sets (umma_step_fixed), the operand swap of the pooled layer is a template
+// argument, single-tap layers unroll two chunks, so the descriptor arithmetic of one step is scheduled under the issue of its
+// neighbour.  Same ring protocol and the same MMAs in the same order as mma_tile (which stays for every other tap count).
+template <bool kTf32, int kSlots, int kTaps, bool kSwap>
+__device__ __forceinline__ void mma_tile_fixed(uint32_t ring_addr, uint32_t full_addr, uint32_t empty_addr, uint32_t d, const TileK k,
+                                               MmaRing<kSlots>& r, unsigned long long& c_wait, unsigned long long& c_step) {
+  constexpr uint32_t idesc = umma_idesc(kTf32 ? 2u : 1u, BM, BN);
+  const uint64_t desc0 = umma_desc_sw128(ring_addr);  // descriptor of slot 0, row 0
+  const uint32_t lo0 = static_cast<uint32_t>(desc0), hi = static_cast<uint32_t>(desc0 >> 32);
+  const uint32_t elected = elect_one() ? 1u : 0u;  // the same lane issues every MMA and commit of the tile
+  uint32_t acc = 0;
+#pragma unroll(kTaps == 1 ? 2 : 1)
+  for (int ch = 0; ch < k.cpt; ++ch) {
+    if (!(r.rdy & 1u)) {
+      XVEC_CNT(const long long t0 = clock64();)
+      mbar_wait_a(full_addr + 8u * r.pos.slot, r.pos.ph, 3);
+      XVEC_CNT(c_wait += clock64() - t0;)
+    }
+    r.rdy &= ~1u;
+    const int a_slot = r.pos.slot;
+    r.pos = r.pos.next();
+    const uint32_t slab_lo = lo0 + static_cast<uint32_t>(a_slot * (SLOT_BYTES >> 4));
+    auto tap_step = [&](auto tap_c) {
+      constexpr int tap = decltype(tap_c)::value;
+      constexpr bool last_tap = tap == kTaps - 1;
+      if (!(r.rdy & 2u)) {
+        XVEC_CNT(const long long t0 = clock64();)
+        mbar_wait_a(full_addr + 8u * r.pos.slot, r.pos.ph, 3);
+        XVEC_CNT(c_wait += clock64() - t0;)
+      }
+      tc_fence_after();
+      const int b_slot = r.pos.slot;
+      r.pos = r.pos.next();
+      const uint32_t x_lo = slab_lo + ((k.tap_off4 >> (4 * tap)) & 15u) * (BK_BYTES >> 4);
+      const uint32_t w_lo = lo0 + static_cast<uint32_t>(b_slot * (SLOT_BYTES >> 4));
+      const RingPos<kSlots> pa = r.pos;
+      const RingPos<kSlots> pb = last_tap ? r.pos.next() : r.pos;
+      XVEC_CNT(const long long ts = clock64();)
+      const uint32_t got = umma_step_fixed<kTf32, last_tap>(elected, d, kSwap ? w_lo : x_lo, kSwap ? x_lo : w_lo, hi, idesc, acc,
+                                                            empty_addr + 8u * a_slot, empty_addr + 8u * b_slot, full_addr + 8u * pa.slot, pa.ph,
+                                                            full_addr + 8u * pb.slot, pb.ph);
+      XVEC_CNT(c_step += clock64() - ts;)
+      r.rdy = last_tap ? got : (got & 2u);
+      acc = 1u;
+    };
+    static_assert(kTaps == 1 || kTaps == 3, "instantiated for the tap counts of the x-vector stack");
+    tap_step(std::integral_constant<int, 0>{});
+    if constexpr (kTaps == 3) {
+      tap_step(std::integral_constant<int, 1>{});
+      tap_step(std::integral_constant<int, 2>{});
     }
   }
 }
@@ -409,8 +470,24 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         const bool pooled = static_cast<int>(item & 7u) == p.n_layers - 1;  // last layer: transposed accumulator (see the epilogue)
         XVEC_CNT(const long long tk = clock64(); const unsigned long long full0 = c_full, step0 = c_step;)
         const TileK tk_(L);
-        if (kAllTf32 || L.tf32) mma_tile<true>(ring_addr, full_addr, empty_addr, d, tk_, ring, pooled, c_full, c_step);
-        else mma_tile<false>(ring_addr, full_addr, empty_addr, d, tk_, ring, pooled, c_full, c_step);
+        auto run = [&](auto tf_c) {
+          constexpr bool tf = decltype(tf_c)::value;
+          if (XVEC_MMA_FIXED && tk_.taps == 1) {
+            if (pooled) mma_tile_fixed<tf, RING_SLOTS, 1, true>(ring_addr, full_addr, empty_addr, d, tk_, ring, c_full, c_step);
+            else mma_tile_fixed<tf, RING_SLOTS, 1, false>(ring_addr, full_addr, empty_addr, d, tk_, ring, c_full, c_step);
+          } else if (XVEC_MMA_FIXED && tk_.taps == 3) {
+            if (pooled) mma_tile_fixed<tf, RING_SLOTS, 3, true>(ring_addr, full_addr, empty_addr, d, tk_, ring, c_full, c_step);
+            else mma_tile_fixed<tf, RING_SLOTS, 3, false>(ring_addr, full_addr, empty_addr, d, tk_, ring, c_full, c_step);
+          } else {
+            mma_tile<tf, RING_SLOTS>(ring_addr, full_addr, empty_addr, d, tk_, ring, pooled, c_full, c_step);
+          }
+        };
+        if constexpr (kAllTf32) {
+          run(std::true_type{});
+        } else {
+          if (L.tf32) run(std::true_type{});
+          else run(std::false_type{});
+        }
         XVEC_CNT(if (lane == 0) {  // per layer: whole K loop, explicit operand waits, time inside the fused issue + probe step
           atomicAdd(p.counter + 40 + (item & 7u), static_cast<unsigned>((clock64() - tk) >> 4));
           atomicAdd(p.counter + 48 + (item & 7u), static_cast<unsigned>((c_full - full0) >> 4));
@@ -524,6 +601,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     // starts (read during iteration it - 1), its global loads are issued first, then item it + 1 is read while they are in
     // flight, and only then does the warp wait for the accumulator.
     // Never sleep on future work with an unpublished tile: a consumer of that tile may be what the future work waits for.
+    XVEC_CNT(unsigned long long e_wait[2] = {0, 0}, e_busy[2] = {0, 0}, e_tail = 0; long long e_t0 = 0, e_t1 = 0;)
     uint32_t item = ring_read(0);
     for (int it = 0;; ++it) {
       if (item == ITEM_DONE) break;
@@ -546,8 +624,10 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         next_item = ring_read(it + 1);
       }
       if (pend && !mbar_test_wait(&tfull_bar[buf], use)) flush();
+      XVEC_CNT(e_t0 = clock64();)
       mbar_wait(&tfull_bar[buf], use, 4);
       tc_fence_after();
+      XVEC_CNT(e_t1 = clock64(); e_wait[pooled_tile ? 0 : 1] += e_t1 - e_t0;)
 #ifdef XVEC_DEBUG
       if (layer > 0 && p.act_ld_bytes) {
         // EXPERIMENT (debug builds, XVEC_STACK_DISCARD=1; measured on B200: DRAM writes per launch 187 MB -> 17.5 MB, but CCTL.RML2
@@ -581,6 +661,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
         released = true;
+        XVEC_CNT(e_t0 = clock64(); e_busy[pooled_tile ? 0 : 1] += e_t0 - e_t1;)
       };
 
       if (XVEC_SDBG(p, 64)) {  // timing experiment: no epilogue at all (no tcgen05.ld, no math, no stores); completion is still published
@@ -658,8 +739,16 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         }
         pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
       }
+      XVEC_CNT(e_tail += clock64() - e_t0;)
       item = next_item;
     }
+    XVEC_CNT(if (rank == 0 && warp == 2 && lane == 0) {  // one epilogue warp per pair: accumulator wait / busy until the release / after it (units of 64 cycles)
+      atomicAdd(p.counter + 12, static_cast<unsigned>(e_wait[0] >> 6));
+      atomicAdd(p.counter + 13, static_cast<unsigned>(e_busy[0] >> 6));
+      atomicAdd(p.counter + 14, static_cast<unsigned>(e_wait[1] >> 6));
+      atomicAdd(p.counter + 15, static_cast<unsigned>(e_busy[1] >> 6));
+      atomicAdd(p.counter + 7, static_cast<unsigned>(e_tail >> 6));
+    })
     if (pend) flush();
     if (lane == 0) tma_store_wait_all();
   }
@@ -853,6 +942,8 @@ static int build_plan(StackPlan& pl, const XvecLayerDesc* tdnn, int n_tdnn, cons
       L.tap_off[j] = d.tap_offsets[j];
       if (d.tap_offsets[j] > max_off) max_off = d.tap_offsets[j];
     }
+    L.tap_off4 = 0;
+    for (int j = 0; j < d.taps; ++j) L.tap_off4 |= static_cast<unsigned>(d.tap_offsets[j]) << (4 * j);
     L.slab_rows = BM_CTA + max_off;
     L.bias = d.bias_dev;
     if (reinterpret_cast<uintptr_t>(d.bias_dev) & 15u) return set_error(XVEC_E_ARG, "bias must be 16-byte aligned");

@@ -59,6 +59,9 @@ for band in args.band.split(","):
         extra = ("  counters(spun,polls,fw,pub,mma_full,mma_tempty)=" + str([c for c in cnt[1:7]])) if any(cnt[1:7]) else ""
         if cnt[9]:
             extra += f" sm_clock={cnt[8] * 64 / cnt[9]:.3f} GHz cta0={cnt[9] / 1e3:.1f} us cta0_cycles={cnt[8] * 64} mma_step_cycles/pair={cnt[10] * 64 // 74} mma_ring_wait/pair={cnt[11] * 64 // 74} mma_full/pair={cnt[5] * 64 // 74} mma_tempty/pair={cnt[6] * 64 // 74}"
+        if cnt[13]:
+            extra += (f" epilogue warp cycles/tile (wait for accumulator, busy until release): pooled {cnt[12] * 64 // 1800} {cnt[13] * 64 // 1800}"
+                      f" stored {cnt[14] * 64 // 2400} {cnt[15] * 64 // 2400} after release (all tiles) {cnt[7] * 64 // 4200}")
         if cnt[9]:
             tiles = [600, 600, 600, 600, 1800]
             ideal = [2560, 12288, 12288, 4096, 4096]
