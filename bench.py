@@ -43,15 +43,16 @@ SEG6_FLOPS = 3_072_000
 LAUNCHES_PER_BATCH = 3  # tdnn_stack_kernel, pool_finalize_kernel, fc_small_kernel (segment6)
 LONG_BATCHES = 2048     # the "long" legs: ~0.6 s of bf16 work per GPU
 WORKLOAD = "c2: 1024 x 3 s utterances (300 x 24 MFCC) per step and GPU as 4 batches of 256, x_vec_extract_layer 6"
-NCU_TENSOR_PIPE = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 78.3, "file": "profiles/r02_stack_ncu_full_summary.txt",
-                   "note": "ncu --set full capture of one tdnn_stack_kernel launch (cold, serialised, 278.3 us at 1.60 GHz); ~7 % of the issued "
+NCU_TENSOR_PIPE = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 77.1, "file": "profiles/r02d_stack_ncu_full_summary.txt",
+                   "note": "ncu --set full capture of one tdnn_stack_kernel launch of the final code (cold, serialised, 260.7 us at 1.73 GHz = 452 k "
+                           "cycles; the capture before the last K-loop change: 78.3 % at 1.60 GHz, 445 k cycles); ~7 % of the issued "
                            "MMA work is padding (don't-care rows of the flat layout, N 1500 -> 1536, K 120 -> 128)"}
 NCU_TENSOR_PIPE_TF32 = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 86.4, "file": "profiles/r02_pool_tf32_ncu_full_summary.txt",
                         "note": "ncu --set full capture of one tdnn_stack_kernel<tf32> launch (497.3 us at 1.59 GHz)"}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tdnn_stack_kernel launch on this workload (ncu --set full; see profiles/README.md)
-STACK_DRAM_BYTES = {"bf16": 185791232,   # 17.1 MB read + 168.7 MB written (final contents of the activation buffers)
+STACK_DRAM_BYTES = {"bf16": 183326976,   # 16.8 MB read + 166.5 MB written (final contents of the activation buffers)
                     "tf32": 697913928}   # 113.2 MB read + 584.7 MB written: float32 activations of a band do not fit in L2
-STACK_DRAM_SOURCE = {"bf16": "profiles/r02_stack_ncu_full_summary.txt", "tf32": "profiles/r02_pool_tf32_ncu_full_summary.txt"}
+STACK_DRAM_SOURCE = {"bf16": "profiles/r02d_stack_ncu_full_summary.txt", "tf32": "profiles/r02_pool_tf32_ncu_full_summary.txt"}
 
 
 def flops_per_utt(t):

@@ -164,10 +164,6 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
 __device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// 16-byte store with an L2 eviction-priority hint (the policies of the TMA traffic, gemm_tile.cuh).
-__device__ __forceinline__ void st_global_v4_hint(void* p, uint4 v, uint64_t l2_policy) {
-  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(l2_policy) : "memory");
-}
 // The 128-byte line at `p` (128-byte aligned) holds dead data: L2 may drop it instead of writing it back to HBM.  Semantically a
 // weak write of an indeterminate value — only ever issued on lines whose last reader has finished and whose next access is a write.
 __device__ __forceinline__ void discard_l2_line(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }

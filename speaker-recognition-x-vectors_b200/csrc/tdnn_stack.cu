@@ -65,12 +65,6 @@ namespace xvec {
 #ifndef XVEC_MMA_FIXED
 #define XVEC_MMA_FIXED 1
 #endif
-// XVEC_DIRECT_STORE = 1: the store epilogue writes the activations with st.global straight from registers (lane pairs exchange
-// halves so that every store instruction writes whole 32-byte sectors); 0: round 1's path through a shared-memory box and a
-// TMA store per tcgen05.ld chunk.  See the epilogue.
-#ifndef XVEC_DIRECT_STORE
-#define XVEC_DIRECT_STORE 1
-#endif
 #ifndef XVEC_RING_SLOTS_BF16
 #define XVEC_RING_SLOTS_BF16 11
 #define XVEC_RING_SLOTS_F32 10
@@ -82,7 +76,7 @@ struct StackCfg {
   static constexpr int BOX_W = kAllTf32 ? 128 : 64;                     // bytes per row of a store box (32 rows x 32 columns)
   static constexpr int BOX_BYTES = 32 * BOX_W;
   static constexpr int NBUF = kAllTf32 ? 1 : XVEC_STAGE_BOXES_BF16;      // store boxes in flight per epilogue warp
-  static constexpr int STAGE_BYTES = XVEC_DIRECT_STORE ? 0 : NBUF * BOX_BYTES;  // store staging per epilogue warp
+  static constexpr int STAGE_BYTES = NBUF * BOX_BYTES;                   // staging per epilogue warp
 };
 constexpr int SLAB_ROWS_MAX = BM_CTA + XVEC_STACK_MAX_TAP_OFFSET;  // frame rows per slab (128 + the largest tap offset, <= 8)
 constexpr int SLAB_BYTES = SLAB_ROWS_MAX * BK_BYTES;  // 17 KiB, a multiple of 1024
@@ -123,8 +117,7 @@ struct StackParams {
   unsigned* ready;            // [(n_layers-1)][m_tiles] completed epilogue-warp stores per tile (zeroed before the launch)
   unsigned* consumed;         // [n_layers][m_tiles] epilogue warps that have seen the tile's MMAs complete (layers >= 1; zeroed)
   char* act[2];               // the two ping-pong activation buffers (layer l >= 1 reads act[(l-1) & 1]) ...
-  long long act_ld_bytes;     // ... their row pitch; 0 = do not discard consumed activations (debug experiment)
-  long long y_ld_bytes;       // row pitch of the activation buffers in bytes (the store epilogue writes act[layer & 1])
+  long long act_ld_bytes;     // ... their row pitch; 0 = do not discard consumed activations 
   int act_es;                 // bytes per activation element
   const int* row_utt;
   const int* blk_slot_base;
@@ -162,7 +155,8 @@ __host__ __device__ inline uint32_t decode_item(const StackParams& p, unsigned i
 // experiments only), 8 short watchdog limit for the dependency spin (2^12 polls instead of 2^24), 16 the dependency watchdog
 // reports its code and stops waiting instead of trapping (a trap is an Xid event on the box; the test only needs the code),
 // 32 / 64 / 128 timing experiments: no activation loads for n-tiles > 0 of single-tap layers / no epilogue work at all / no weight
-// loads for those tiles.
+// loads for those tiles (use 32 and 128 together, = 160: with the two producer warps of round 2 one of them alone stalls the
+// launch until the watchdog fires).
 // Debug builds also accumulate counters in the spare words of the control block (read by tools/stack_bench.py; units of 64
 // cycles unless stated): 1 tiles whose dependency warp had to spin on a flag (count), 2 flag polls (count), 3 producer waiting
 // for its dependency warp, 4 producer waiting for the work item, 5 MMA warp waiting for operands (explicit waits only),
@@ -322,10 +316,7 @@ template <bool kAllTf32>
 constexpr int stack_smem_bytes() { return 1024 + StackCfg<kAllTf32>::SLOTS * SLOT_BYTES + EPI_WARPS * StackCfg<kAllTf32>::STAGE_BYTES; }
 static_assert(stack_smem_bytes<false>() <= 227 * 1024 - 1024 && stack_smem_bytes<true>() <= 227 * 1024 - 1024,
               "operand ring + store staging (+ 1 KiB of static barriers) exceed the 227 KiB of shared memory a CTA can have");
-#ifndef XVEC_SMEM_LEFT_FOR_TAIL_KIB
-#define XVEC_SMEM_LEFT_FOR_TAIL_KIB 20
-#endif
-constexpr int STACK_SMEM_LEFT_FOR_TAIL = XVEC_SMEM_LEFT_FOR_TAIL_KIB * 1024;  // what a co-resident tail kernel may use (fc_small.cu, seg_fused.cu assert against it)
+constexpr int STACK_SMEM_LEFT_FOR_TAIL = 20 * 1024;  // what a co-resident tail kernel may use (fc_small.cu, seg_fused.cu assert against it)
 static_assert(228 * 1024 - stack_smem_bytes<false>() - 2048 - 2 * 1024 >= STACK_SMEM_LEFT_FOR_TAIL &&
               228 * 1024 - stack_smem_bytes<true>() - 2048 - 2 * 1024 >= STACK_SMEM_LEFT_FOR_TAIL,
               "the stack kernel must leave room on the SM for the tail kernels of the previous batch");
@@ -341,9 +332,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte alignment
-#if !XVEC_DIRECT_STORE
   uint8_t* epi_smem = base + RING_SLOTS * SLOT_BYTES;
-#endif
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -353,9 +342,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     for (int l = 0; l < p.n_layers; ++l) {
       tma_prefetch_desc(&maps.a[l]);
       tma_prefetch_desc(&maps.b[l]);
-#if !XVEC_DIRECT_STORE
       if (l + 1 < p.n_layers) tma_prefetch_desc(&maps.y[l]);
-#endif
     }
     for (int s = 0; s < RING_SLOTS; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx (bytes of both CTAs)
@@ -594,33 +581,22 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
     const int cbeg = ((warp - 2) >> 2) * (BN / 2);  // this warp's half of the tile's columns
     const int cend = cbeg + BN / 2;
-#if !XVEC_DIRECT_STORE
     uint8_t* out_stage = epi_smem + (warp - 2) * StackCfg<kAllTf32>::STAGE_BYTES;
     int store_seq = 0;
-#endif
     // Store staging: one TMA-store box per tcgen05.ld chunk (32 rows x 32 columns).  bf16: 64-byte rows (SWIZZLE_64B), the warp's
     // 4 KiB hold two boxes, so staging chunk k+1 overlaps the store of chunk k; float32: 128-byte rows, one box.
     constexpr int BOX_W = kAllTf32 ? 128 : 64;                              // bytes per box row
     constexpr int BOX_BYTES = 32 * BOX_W;
     constexpr int NBUF = StackCfg<kAllTf32>::NBUF;                          // boxes in flight per warp
-    constexpr int BOXES = (BN / 2) / 32;                                    // 32-column chunks (TMA path: boxes = bulk groups) per tile and warp
+    constexpr int BOXES = (BN / 2) / 32;                                    // boxes (= bulk groups) per tile and warp
     unsigned* pend = nullptr;  // ready counter of the last stored tile whose completion has not been published yet (warp-uniform)
     // Publish `pend`: lane 0 owns the warp's bulk groups; once they are complete the tile's rows are in global memory.
     auto flush = [&]() {
-#if XVEC_DIRECT_STORE
-      // every lane wrote its share of the tile with generic-proxy stores; the consumers read it through the async proxy (TMA)
-      if (!XVEC_SDBG(p, 2)) {
-        if (!XVEC_SDBG(p, 4)) fence_proxy_async_all();
-        __syncwarp();
-        if (lane == 0) red_release_gpu_add_u32(pend, 1u);
-      }
-#else
       if (lane == 0 && !XVEC_SDBG(p, 2)) {
         tma_store_wait_all();
         if (!XVEC_SDBG(p, 4)) fence_proxy_async_all();
         red_release_gpu_add_u32(pend, 1u);
       }
-#endif
       pend = nullptr;
     };
     // The epilogue warps' per-tile chain — read the work item (~500 cycles), wait for the accumulator, fetch the pooling
@@ -706,76 +682,6 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         if (!released) release_tmem();
         if (pend) flush();  // its stores were issued a whole tile ago
       } else {
-#if XVEC_DIRECT_STORE
-        // Straight from registers: after tcgen05.ld a lane holds 32 consecutive channels of ONE frame row — 64 contiguous bytes
-        // in bf16 (four 16-byte pieces), 128 in float32 (eight).  Lanes 2i / 2i+1 exchange pieces so that each st.global.v4 of the
-        // warp writes 16 rows x 32 contiguous bytes, i.e. whole sectors (two lanes per sector), first the even lane's row, then
-        // the odd lane's.  No shared-memory staging, no bulk groups to wait for: round 1's path (a 2 KiB box and a TMA store per
-        // chunk, each waiting for the previous store to have read the box) took ~6 300 cycles per tile and warp — more than the
-        // K loop of a TDNN1 (2 560) or TDNN4 (4 096) tile, whose accumulators the MMA warp then waited for — against the ~2 050
-        // cycles the TMEM reads of a tile need (64 B per clock and SM).
-        constexpr int PIECES = kAllTf32 ? 8 : 4;  // 16-byte pieces per row of a 32-column chunk
-        const bool odd = lane & 1;
-        char* const ye = p.act[layer & 1] + static_cast<long long>(row0 + (lane & ~1)) * p.y_ld_bytes + (odd ? 16 : 0);
-        char* const yo = ye + p.y_ld_bytes;
-        const bool ok_e = row0 + (lane & ~1) < p.rows, ok_o = row0 + (lane | 1) < p.rows;  // rows past the matrix are not stored
-        const unsigned long long pol_y = p.pol_y;
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(tbase + cbeg, va);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < BOXES; ++k) {
-          uint32_t(&v)[32] = (k & 1) ? vb : va;
-          if (k + 1 < BOXES) tmem_ld_32x32(tbase + cbeg + 32 * (k + 1), (k & 1) ? va : vb);
-          const int col0 = n0 + cbeg + k * 32;
-          // r = relu(acc + bias') — every BatchNorm is folded forward into the next layer's weights (xvector.py)
-          float o[32];
-          const float4* bp = reinterpret_cast<const float4*>(L.bias + col0);
-#pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 bb = __ldg(bp + (j4 >> 2));
-            const float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 0]), __uint_as_float(v[j4 + 1])), make_float2(bb.x, bb.y));
-            const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), make_float2(bb.z, bb.w));
-            o[j4 + 0] = a.x; o[j4 + 1] = a.y; o[j4 + 2] = d.x; o[j4 + 3] = d.y;
-          }
-          uint4 w[PIECES];
-          if constexpr (!kAllTf32) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              w[j].x = pack_bf16x2_relu(o[8 * j + 0], o[8 * j + 1]);
-              w[j].y = pack_bf16x2_relu(o[8 * j + 2], o[8 * j + 3]);
-              w[j].z = pack_bf16x2_relu(o[8 * j + 4], o[8 * j + 5]);
-              w[j].w = pack_bf16x2_relu(o[8 * j + 6], o[8 * j + 7]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              w[j].x = __float_as_uint(fmaxf(o[4 * j + 0], 0.f));
-              w[j].y = __float_as_uint(fmaxf(o[4 * j + 1], 0.f));
-              w[j].z = __float_as_uint(fmaxf(o[4 * j + 2], 0.f));
-              w[j].w = __float_as_uint(fmaxf(o[4 * j + 3], 0.f));
-            }
-          }
-          const int cb = col0 * (kAllTf32 ? 4 : 2);  // byte offset of the chunk in its row
-#pragma unroll
-          for (int j = 0; j < PIECES / 2; ++j) {
-            // the even lane keeps its piece 2j and gets the odd lane's piece 2j; the odd lane keeps its 2j+1 and gets the even lane's
-            const uint4 give = odd ? w[2 * j] : w[2 * j + 1];
-            uint4 got;
-            got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
-            got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
-            got.z = __shfl_xor_sync(0xffffffffu, give.z, 1);
-            got.w = __shfl_xor_sync(0xffffffffu, give.w, 1);
-            const uint4 de = odd ? got : w[2 * j];        // row of the even lane: pieces 2j (even lane) and 2j+1 (odd lane)
-            const uint4 dq = odd ? w[2 * j + 1] : got;    // row of the odd lane
-            if (ok_e) st_global_v4_hint(ye + cb + 32 * j, de, pol_y);
-            if (ok_o) st_global_v4_hint(yo + cb + 32 * j, dq, pol_y);
-          }
-          if (k + 1 < BOXES) tmem_ld_wait();
-          if (k == BOXES - 2) release_tmem();  // the last tcgen05.ld of the tile has landed
-        }
-        if (pend) flush();  // the previous stored tile (its stores are a whole tile old)
-#else
         const CUtensorMap* my = &maps.y[layer];
         // tcgen05.ld of chunk k+1 is in flight while chunk k is converted, staged and stored
         uint32_t va[32], vb[32];
@@ -835,7 +741,6 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
             red_release_gpu_add_u32(pend, 1u);
           }
         }
-#endif
         pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
       }
       XVEC_CNT(e_tail += clock64() - e_t0;)
@@ -849,9 +754,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       atomicAdd(p.counter + 7, static_cast<unsigned>(e_tail >> 6));
     })
     if (pend) flush();
-#if !XVEC_DIRECT_STORE
     if (lane == 0) tma_store_wait_all();
-#endif
   }
 
   tc_fence_before();
@@ -1163,7 +1066,6 @@ int stack_dispatch(const XvecLayerDesc* tdnn, int n_tdnn, const void* x, int64_t
   p.act[1] = static_cast<char*>(act1);
   p.act_es = tdnn[1].dtype == XVEC_BF16 ? 2 : 4;
   p.act_ld_bytes = 0;
-  p.y_ld_bytes = act_ld * p.act_es;
   p.row_utt = row_utt;
   p.blk_slot_base = blk_slot_base;
   p.part = part;
