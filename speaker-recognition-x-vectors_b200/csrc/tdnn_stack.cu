@@ -154,9 +154,8 @@ __host__ __device__ inline uint32_t decode_item(const StackParams& p, unsigned i
 // tests/test_gpu_kernels.py::test_watchdog_code_is_readable uses), 4 skip the proxy fences (results are then undefined; timing
 // experiments only), 8 short watchdog limit for the dependency spin (2^12 polls instead of 2^24), 16 the dependency watchdog
 // reports its code and stops waiting instead of trapping (a trap is an Xid event on the box; the test only needs the code),
-// 32 / 64 / 128 timing experiments: no activation loads for n-tiles > 0 of single-tap layers / no epilogue work at all / no weight
-// loads for those tiles (use 32 and 128 together, = 160: with the two producer warps of round 2 one of them alone stalls the
-// launch until the watchdog fires).
+// 64 timing experiment: no epilogue work at all.  (Bits 32 / 128 — no activation / weight loads for n-tiles > 0 of single-tap layers —
+// were removed after their measurements, profiles/r02_experiments.txt: with two producer warps they no longer ran reliably.)
 // Debug builds also accumulate counters in the spare words of the control block (read by tools/stack_bench.py; units of 64
 // cycles unless stated): 1 tiles whose dependency warp had to spin on a flag (count), 2 flag polls (count), 3 producer waiting
 // for its dependency warp, 4 producer waiting for the work item, 5 MMA warp waiting for operands (explicit waits only),
@@ -418,14 +417,10 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         const CUtensorMap* ma = &maps.a[layer];
         const uint32_t slab_tx = 2u * static_cast<uint32_t>(L.slab_rows) * BK_BYTES;  // bytes of both CTAs' slabs
         const unsigned long long pol_a = p.pol_a;
-        // timing experiment (debug bit 32): no activation loads for n-tiles > 0 of single-tap layers, as if the m-tile's
-        // activation chunks were resident in shared memory (the MMAs then read stale slots: wrong results, right timing)
-        const bool skip_a = XVEC_SDBG(p, 32) && taps == 1 && nt > 0;
         for (int ch = 0; ch < cpt; ++ch) {
           if (!rdy) mbar_wait_a(empty_addr + 8u * pos.slot, pos.ph ^ 1u, 1);
           const RingPos<RING_SLOTS> nxt = pos.skip(1 + taps);  // the next chunk's slab, also across a tile boundary
-          if (skip_a && rank == 0 && elect_one()) mbar_expect_tx_a(full_addr + 8u * pos.slot, 0);  // completes the phase with no bytes
-          rdy = tma_step_one(elect_one() ? 1u : 0u, is_leader, skip_a ? 0u : 1u, full_addr + 8u * pos.slot, full_leader + 8u * pos.slot, slab_tx,
+          rdy = tma_step_one(elect_one() ? 1u : 0u, is_leader, 1u, full_addr + 8u * pos.slot, full_leader + 8u * pos.slot, slab_tx,
                              ring_addr + pos.slot * SLOT_BYTES, ma, ch * bke, m0, pol_a, empty_addr + 8u * nxt.slot, nxt.ph ^ 1u);
           pos = nxt;
         }
@@ -433,15 +428,13 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         const int n0 = nt * BN + static_cast<int>(rank) * BN_CTA;
         const CUtensorMap* mb = &maps.b[layer];
         const unsigned long long pol_b = p.pol_b;
-        const bool skip_b = XVEC_SDBG(p, 128) && taps == 1 && nt > 0;  // (debug bit 128) the same for the weight tiles
         for (int ch = 0; ch < cpt; ++ch) {
           RingPos<RING_SLOTS> pb = pos.next();  // the chunk's first weight tile sits behind its slab
           int b_row = ch * n_pad + n0;          // row of the (tap, chunk) tile in the chunk-major packed matrix: (tap * cpt + ch) * n_pad + n0
           for (int tap = 0; tap < taps; ++tap, b_row += cpt * n_pad) {
             if (!rdy) mbar_wait_a(empty_addr + 8u * pb.slot, pb.ph ^ 1u, 1);
             const RingPos<RING_SLOTS> nxt = tap == taps - 1 ? pb.skip(2) : pb.next();  // after the last tap: over the next chunk's slab
-            if (skip_b && rank == 0 && elect_one()) mbar_expect_tx_a(full_addr + 8u * pb.slot, 0);
-            rdy = tma_step_one(elect_one() ? 1u : 0u, is_leader, skip_b ? 0u : 1u, full_addr + 8u * pb.slot, full_leader + 8u * pb.slot, 2u * B_BYTES,
+            rdy = tma_step_one(elect_one() ? 1u : 0u, is_leader, 1u, full_addr + 8u * pb.slot, full_leader + 8u * pb.slot, 2u * B_BYTES,
                                ring_addr + pb.slot * SLOT_BYTES, mb, 0, b_row, pol_b, empty_addr + 8u * nxt.slot, nxt.ph ^ 1u);
             pb = nxt;
           }
