@@ -259,3 +259,48 @@ def test_wide_context_falls_back_to_per_layer_launches(xb, precision):
     cos = torch.nn.functional.cosine_similarity(got, xv_ref, dim=1)
     assert cos.min().item() > 0.9999
     assert torch.isfinite(m.forward(x.cuda())).all()
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_other_tap_counts_run_in_the_stack_kernel(xb, precision):
+    """The one-launch kernel specialises its MMA loop for the tap counts of the reference's stack (1 and 3; main.py:39-43) and keeps
+    a generic loop for every other context get_time_context accepts (tdnn_layer.py:43-60).  A stack with a 2-tap layer
+    ([-2, 2], extra/time_context_test.py:25), a 5-tap 512-channel layer and a 3-tap POOLED last layer stays on the stack kernel
+    (tap spans <= 8) and must agree with a plain torch fp64 statement of the reference's op sequence."""
+    torch.manual_seed(5)
+    m = xb.XVectorModel(precision=precision)
+    m.time_context_layers[1] = xb.TdnnLayer(input_size=512, output_size=512, context=[-2, 2])
+    m.time_context_layers[2] = xb.TdnnLayer(input_size=512, output_size=512, context=[-2, -1, 0, 1, 2])
+    m.time_context_layers[4] = xb.TdnnLayer(input_size=512, output_size=1500, context=[-1, 0, 1])
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        for layer in m.time_context_layers:
+            layer.norm.running_mean.copy_(0.3 * torch.randn(layer.norm.num_features, generator=g))
+            layer.norm.running_var.copy_(0.5 + torch.rand(layer.norm.num_features, generator=g))
+    m = m.cuda().eval()
+    assert m._stack_kernel_ok() and m.lost_frames == 4 + 4 + 4 + 0 + 2
+    x = torch.randn(5, 150, 24, generator=g)
+
+    def ref_forward(x):
+        h = x.double()
+        for layer in m.time_context_layers:
+            offs = xb.tap_offsets(layer.context)
+            t_out = h.shape[1] - offs[-1]
+            u = torch.cat([h[:, o:o + t_out] for o in offs], 2)
+            h = torch.relu(u @ layer.linear.weight.double().cpu().t() + layer.linear.bias.double().cpu())
+            n = layer.norm
+            h = (h - n.running_mean.double().cpu()) / torch.sqrt(n.running_var.double().cpu() + n.eps) * n.weight.double().cpu() + n.bias.double().cpu()
+        pooled = torch.cat((h.mean(1), h.std(1)), 1)
+        return pooled, pooled @ m.segment_layer6.weight.double().cpu().t() + m.segment_layer6.bias.double().cpu()
+
+    with torch.no_grad():
+        pooled_ref, xv_ref = ref_forward(x)
+    got = m.extract_x_vec(x.cuda()).double().cpu()
+    pooled, _ = m.pooled_stats_flat(x.reshape(-1, 24).cuda(), [150] * 5)
+    pooled = pooled.double().cpu()
+    tol = 1e-3 if precision == "tf32" else 3e-2
+    assert ((got - xv_ref).abs().max(1).values / xv_ref.norm(dim=1)).max().item() < tol
+    assert ((pooled - pooled_ref).abs().max(1).values / pooled_ref.norm(dim=1)).max().item() < tol
+    cos = torch.nn.functional.cosine_similarity(got, xv_ref, dim=1)
+    assert cos.min().item() > 0.9999
+    assert xb._lib.load().xvec_watchdog_code() == 0
