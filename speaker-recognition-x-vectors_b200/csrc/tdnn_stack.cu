@@ -739,7 +739,8 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       XVEC_CNT(e_tail += clock64() - e_t0;)
       item = next_item;
     }
-    XVEC_CNT(if (rank == 0 && warp == 2 && lane == 0) {  // one epilogue warp per pair: accumulator wait / busy until the release / after it (units of 64 cycles)
+    // which epilogue warp reports: XVEC_STACK_DBG bits [8,12) = warp (0: warp 2), bit 13 = CTA rank of the pair
+    XVEC_CNT(if (static_cast<int>(rank) == ((p.dbg >> 13) & 1) && warp == (((p.dbg >> 8) & 15) ? ((p.dbg >> 8) & 15) : 2) && lane == 0) {  // one epilogue warp per pair: accumulator wait / busy until the release / after it (units of 64 cycles)
       atomicAdd(p.counter + 12, static_cast<unsigned>(e_wait[0] >> 6));
       atomicAdd(p.counter + 13, static_cast<unsigned>(e_busy[0] >> 6));
       atomicAdd(p.counter + 14, static_cast<unsigned>(e_wait[1] >> 6));
