@@ -298,6 +298,15 @@ __device__ __forceinline__ uint32_t tma_step_one(uint32_t elected, uint32_t is_l
   return rdy;
 }
 
+// A bare CTA-pair tensor load (no arming of the barrier): the bytes complete on the leader's barrier `bar_leader`, which the
+// caller has armed for them.  Used by a timing experiment of the debug build only (tdnn_stack.cu, XVEC_STACK_DBG bit 32).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t bar_leader, uint32_t smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_leader), "l"(pol)
+      : "memory");
+}
+
 enum { STEP_COMMIT_A = 1, STEP_COMMIT_B = 2, STEP_PROBE_A = 4, STEP_PROBE_B = 8 };
 template <bool kTf32>
 __device__ __forceinline__ uint32_t umma_step_pair(uint32_t elected, uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,

@@ -154,8 +154,10 @@ __host__ __device__ inline uint32_t decode_item(const StackParams& p, unsigned i
 // tests/test_gpu_kernels.py::test_watchdog_code_is_readable uses), 4 skip the proxy fences (results are then undefined; timing
 // experiments only), 8 short watchdog limit for the dependency spin (2^12 polls instead of 2^24), 16 the dependency watchdog
 // reports its code and stops waiting instead of trapping (a trap is an Xid event on the box; the test only needs the code),
-// 64 timing experiment: no epilogue work at all.  (Bits 32 / 128 — no activation / weight loads for n-tiles > 0 of single-tap layers —
-// were removed after their measurements, profiles/r02_experiments.txt: with two producer warps they no longer ran reliably.)
+// 32 timing experiment: every activation slab is loaded twice (more shared-memory write traffic, same results), 64 timing
+// experiment: no epilogue work at all.  (The round's earlier bits 32 / 128 — no activation / weight loads for n-tiles > 0 of
+// single-tap layers — were removed after their measurements, profiles/r02_experiments.txt: with two producer warps they no longer
+// ran reliably.)
 // Debug builds also accumulate counters in the spare words of the control block (read by tools/stack_bench.py; units of 64
 // cycles unless stated): 1 tiles whose dependency warp had to spin on a flag (count), 2 flag polls (count), 3 producer waiting
 // for its dependency warp, 4 producer waiting for the work item, 5 MMA warp waiting for operands (explicit waits only),
@@ -415,13 +417,17 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         const int bke = (kAllTf32 || L.tf32) ? 32 : 64;  // elements per 128-byte chunk
         const int m0 = mt * BM + static_cast<int>(rank) * BM_CTA;
         const CUtensorMap* ma = &maps.a[layer];
-        const uint32_t slab_tx = 2u * static_cast<uint32_t>(L.slab_rows) * BK_BYTES;  // bytes of both CTAs' slabs
+        // timing experiment (debug bit 32): every activation slab is loaded TWICE into its slot (same bytes, same place; the barrier
+        // is armed for both) — +50 % / +26 % shared-memory write traffic on single-tap / 3-tap layers, results unchanged
+        const bool twice = XVEC_SDBG(p, 32);
+        const uint32_t slab_tx = (twice ? 4u : 2u) * static_cast<uint32_t>(L.slab_rows) * BK_BYTES;  // bytes of both CTAs' slabs
         const unsigned long long pol_a = p.pol_a;
         for (int ch = 0; ch < cpt; ++ch) {
           if (!rdy) mbar_wait_a(empty_addr + 8u * pos.slot, pos.ph ^ 1u, 1);
           const RingPos<RING_SLOTS> nxt = pos.skip(1 + taps);  // the next chunk's slab, also across a tile boundary
           rdy = tma_step_one(elect_one() ? 1u : 0u, is_leader, 1u, full_addr + 8u * pos.slot, full_leader + 8u * pos.slot, slab_tx,
                              ring_addr + pos.slot * SLOT_BYTES, ma, ch * bke, m0, pol_a, empty_addr + 8u * nxt.slot, nxt.ph ^ 1u);
+          if (twice && elect_one()) tma_load_2d_pair(full_leader + 8u * pos.slot, ring_addr + pos.slot * SLOT_BYTES, ma, ch * bke, m0, pol_a);
           pos = nxt;
         }
       } else {
