@@ -173,7 +173,21 @@ __device__ __forceinline__ uint32_t atom_add_relaxed_gpu_u32(uint32_t* p, uint32
   return old;
 }
 // Orders generic-proxy accesses (the flag acquire / release) against async-proxy accesses (TMA loads / stores) of this thread.
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// The data behind the flags (activation tiles) lives in GLOBAL memory, so the fence is restricted to that state space: ptxas
+// emits FENCE.VIEW.ASYNC.G for it, while the unrestricted `fence.proxy.async` is MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC.S — a
+// GPU-scope memory barrier of ~1 000 cycles that sat in the dependency warp's per-tile chain (scheduler -> flags -> fence ->
+// producer may start) and in every publication of a stored tile (measured: 287 -> 281 us per launch in the debug build with
+// the fences switched off; profiles/r02_experiments.txt).  XVEC_PROXY_FENCE_ALL = 1 restores the unrestricted form.
+#ifndef XVEC_PROXY_FENCE_ALL
+#define XVEC_PROXY_FENCE_ALL 0
+#endif
+__device__ __forceinline__ void fence_proxy_async_global() {
+#if XVEC_PROXY_FENCE_ALL
+  asm volatile("fence.proxy.async;" ::: "memory");
+#else
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+}
 
 // ----------------------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {

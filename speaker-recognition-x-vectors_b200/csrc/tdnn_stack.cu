@@ -566,7 +566,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
           }
         }
         XVEC_CNT(c_polls += spins; c_spun += spins ? 1 : 0;)
-        if (!XVEC_SDBG(p, 4)) fence_proxy_async_all();
+        if (!XVEC_SDBG(p, 4)) fence_proxy_async_global();
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&dep_bar[it % SCHED_SLOTS]);
@@ -593,7 +593,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     auto flush = [&]() {
       if (lane == 0 && !XVEC_SDBG(p, 2)) {
         tma_store_wait_all();
-        if (!XVEC_SDBG(p, 4)) fence_proxy_async_all();
+        if (!XVEC_SDBG(p, 4)) fence_proxy_async_global();
         red_release_gpu_add_u32(pend, 1u);
       }
       pend = nullptr;
@@ -736,7 +736,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         if (pend) {  // the previous stored tile's groups are older than this tile's BOXES groups
           if (lane == 0 && !XVEC_SDBG(p, 2)) {
             tma_store_wait_done<BOXES>();
-            if (!XVEC_SDBG(p, 4)) fence_proxy_async_all();
+            if (!XVEC_SDBG(p, 4)) fence_proxy_async_global();
             red_release_gpu_add_u32(pend, 1u);
           }
         }
