@@ -132,6 +132,18 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void st_shared_cluster_u32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
 }
+// The same hand-off without a cluster-scope release / acquire pair: the word travels as an ASYNC store that completes 4 bytes of
+// transaction on the peer's barrier (st.async ... mbarrier::complete_tx::bytes), which the writer has armed with a remote
+// arrive.expect_tx.  Observing the phase completion makes the word visible (the mbarrier's transaction mechanism, as for TMA
+// loads), so the reader waits with an ordinary try_wait.  ptxas implements `mbarrier.arrive.release.cluster` as MEMBAR.ALL.GPU and
+// every `try_wait.acquire.cluster` as CCTL.IVALL (an L1 invalidation): one GPU-scope barrier per work item in the scheduler warp
+// and twelve L1 invalidations per work item in the peer CTA went away with this.
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_async_cluster_u32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v), "r"(cluster_mbar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }

@@ -65,6 +65,11 @@ namespace xvec {
 #ifndef XVEC_MMA_FIXED
 #define XVEC_MMA_FIXED 1
 #endif
+// XVEC_ITEM_ST_ASYNC = 1: the scheduler hands a work item to the peer CTA with st.async + the barrier's transaction count instead
+// of st.shared::cluster + a release.cluster arrive / acquire.cluster waits (ptx.cuh: st_async_cluster_u32).
+#ifndef XVEC_ITEM_ST_ASYNC
+#define XVEC_ITEM_ST_ASYNC 1
+#endif
 #ifndef XVEC_RING_SLOTS_BF16
 #define XVEC_RING_SLOTS_BF16 11
 #define XVEC_RING_SLOTS_F32 10
@@ -376,8 +381,12 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   auto ring_read = [&](int it) -> uint32_t {
     const int slot = it % SCHED_SLOTS;
     const uint32_t sph = (it / SCHED_SLOTS) & 1u;
+#if XVEC_ITEM_ST_ASYNC
+    mbar_wait(&sfull_bar[slot], sph, 6);  // leader: the scheduler's arrive; peer: the 4 bytes of the scheduler's st.async have landed
+#else
     if (rank == 0) mbar_wait(&sfull_bar[slot], sph, 6);
     else mbar_wait_cluster(&sfull_bar[slot], sph, 6);
+#endif
     const uint32_t item = *reinterpret_cast<volatile uint32_t*>(&sched_item[slot]);
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sempty_bar[slot]), 0));
@@ -540,9 +549,15 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
         mbar_wait(&sempty_bar[slot], sph ^ 1u, 5);
         if (lane == 0) {
           sched_item[slot] = item;
-          st_shared_cluster_u32(mapa_u32(smem_u32(&sched_item[slot]), 1), item);
           mbar_arrive(&sfull_bar[slot]);
+#if XVEC_ITEM_ST_ASYNC
+          const uint32_t peer_bar = mapa_u32(smem_u32(&sfull_bar[slot]), 1);
+          mbar_arrive_expect_tx_cluster(peer_bar, 4);
+          st_async_cluster_u32(mapa_u32(smem_u32(&sched_item[slot]), 1), item, peer_bar);
+#else
+          st_shared_cluster_u32(mapa_u32(smem_u32(&sched_item[slot]), 1), item);
           mbar_arrive_release_cluster(mapa_u32(smem_u32(&sfull_bar[slot]), 1));
+#endif
         }
         __syncwarp();
       } else {
