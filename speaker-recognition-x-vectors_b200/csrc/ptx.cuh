@@ -176,6 +176,13 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
 __device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Shared-memory counter with acquire + release at CTA scope: what the arriving threads did before is visible to the one that
+// sees the last count.
+__device__ __forceinline__ uint32_t atom_add_acq_rel_cta_shared_u32(uint32_t smem_addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_addr), "r"(v) : "memory");
+  return old;
+}
 // The 128-byte line at `p` (128-byte aligned) holds dead data: L2 may drop it instead of writing it back to HBM.  Semantically a
 // weak write of an indeterminate value — only ever issued on lines whose last reader has finished and whose next access is a write.
 __device__ __forceinline__ void discard_l2_line(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }

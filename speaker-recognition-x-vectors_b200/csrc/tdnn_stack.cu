@@ -70,6 +70,9 @@ namespace xvec {
 #ifndef XVEC_ITEM_ST_ASYNC
 #define XVEC_ITEM_ST_ASYNC 1
 #endif
+#ifndef XVEC_PUBLISH_PER_CTA
+#define XVEC_PUBLISH_PER_CTA 1  // one gpu-scope release per stored tile and CTA (the last of its 8 epilogue warps) instead of one per warp
+#endif
 #ifndef XVEC_RING_SLOTS_BF16
 #define XVEC_RING_SLOTS_BF16 11
 #define XVEC_RING_SLOTS_F32 10
@@ -92,6 +95,7 @@ constexpr int CREDIT_BARS = 4;            // "tile started" barriers; the schedu
 constexpr int STACK_RUNAHEAD = 1;         // items a pair may hold that its producer has not started (p.runahead); measured: 1, 2, 3 give the same launch time
 constexpr uint32_t ITEM_DONE = 0xFFFFFFFFu;
 constexpr int SCHED_CONSUMERS = 2 * EPI_WARPS + 6;  // per slot: the two producer warps of both CTAs, leader MMA warp, peer dependency warp, 8 epilogue warps of each CTA
+static_assert((EPI_WARPS & (EPI_WARPS - 1)) == 0, "publish() counts the epilogue warps of a CTA modulo EPI_WARPS");
 constexpr int DEP_WARP = 2 + EPI_WARPS;             // warp 10
 constexpr int WPROD_WARP = DEP_WARP + 1;            // warp 11: the weight-tile producer (warp 0 loads the activation slabs)
 constexpr int STACK_THREADS = GEMM_THREADS + 64;
@@ -335,6 +339,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   __shared__ uint64_t full_bar[RING_SLOTS], empty_bar[RING_SLOTS], tfull_bar[2], tempty_bar[2];
   __shared__ uint64_t sfull_bar[SCHED_SLOTS], sempty_bar[SCHED_SLOTS], dep_bar[SCHED_SLOTS], credit_bar[CREDIT_BARS];
   __shared__ uint32_t sched_item[SCHED_SLOTS];
+  __shared__ uint32_t pub_cnt[4];  // epilogue warps that have completed the stores of a tile, per tile in flight (free-running, see publish)
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024-byte alignment
@@ -345,6 +350,7 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
   const uint32_t rank = cluster_ctarank();  // 0 = leader of the pair
 
   if (warp == 0 && lane == 0) {
+    for (int c = 0; c < 4; ++c) pub_cnt[c] = 0;
     for (int l = 0; l < p.n_layers; ++l) {
       tma_prefetch_desc(&maps.a[l]);
       tma_prefetch_desc(&maps.b[l]);
@@ -604,15 +610,30 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     constexpr int NBUF = StackCfg<kAllTf32>::NBUF;                          // boxes in flight per warp
     constexpr int BOXES = (BN / 2) / 32;                                    // boxes (= bulk groups) per tile and warp
     unsigned* pend = nullptr;  // ready counter of the last stored tile whose completion has not been published yet (warp-uniform)
-    // Publish `pend`: lane 0 owns the warp's bulk groups; once they are complete the tile's rows are in global memory.
-    auto flush = [&]() {
+    int pend_it = 0;           // ... and the work-item index it was processed at (all epilogue warps of a CTA see the same sequence)
+    // Publish `pend`: lane 0 owns the warp's bulk groups; once they are complete the tile's rows are in global memory.  The eight
+    // epilogue warps of a CTA count themselves in shared memory (acq_rel at CTA scope), and the LAST one to arrive publishes for
+    // all: one fence + one red.release.gpu (+ 8) per tile and CTA instead of eight — a gpu-scope release is a MEMBAR.ALL.GPU.
+    // A tile's counter is free-running (8 arrivals per use; at most three stored tiles of a CTA are unpublished at any time: a
+    // warp publishes tile i before it leaves tile i + 1, and nobody enters tile i + 2 before every warp has released tile i).
+    // kAll: wait for every bulk group of this thread; otherwise for all but the BOXES most recent (the current tile's).
+    auto publish = [&](bool all) {
       if (lane == 0 && !XVEC_SDBG(p, 2)) {
-        tma_store_wait_all();
+        if (all) tma_store_wait_all();
+        else tma_store_wait_done<BOXES>();
+#if XVEC_PUBLISH_PER_CTA
+        if ((atom_add_acq_rel_cta_shared_u32(smem_u32(&pub_cnt[pend_it & 3]), 1u) & (EPI_WARPS - 1)) == EPI_WARPS - 1) {
+          if (!XVEC_SDBG(p, 4)) fence_proxy_async_global();
+          red_release_gpu_add_u32(pend, static_cast<uint32_t>(EPI_WARPS));
+        }
+#else
         if (!XVEC_SDBG(p, 4)) fence_proxy_async_global();
         red_release_gpu_add_u32(pend, 1u);
+#endif
       }
       pend = nullptr;
     };
+    auto flush = [&]() { publish(true); };
     // The epilogue warps' per-tile chain — read the work item (~500 cycles), wait for the accumulator, fetch the pooling
     // bookkeeping from L2 (~700 cycles), then four dependent tcgen05.ld + math rounds — is what the MMA warp ends up waiting
     // for once the mainloop is fast (round 2).  So the chain is software-pipelined: item `it` is in hand when iteration `it`
@@ -685,7 +706,10 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
       if (XVEC_SDBG(p, 64)) {  // timing experiment: no epilogue at all (no tcgen05.ld, no math, no stores); completion is still published
         release_tmem();
         if (pend) flush();
-        if (layer != p.n_layers - 1) pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
+        if (layer != p.n_layers - 1) {
+          pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
+          pend_it = it;
+        }
         item = next_item;
         continue;
       }
@@ -748,14 +772,9 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
           }
           ++store_seq;
         }
-        if (pend) {  // the previous stored tile's groups are older than this tile's BOXES groups
-          if (lane == 0 && !XVEC_SDBG(p, 2)) {
-            tma_store_wait_done<BOXES>();
-            if (!XVEC_SDBG(p, 4)) fence_proxy_async_global();
-            red_release_gpu_add_u32(pend, 1u);
-          }
-        }
+        if (pend) publish(false);  // the previous stored tile's groups are older than this tile's BOXES groups
         pend = p.ready + static_cast<size_t>(layer) * p.m_tiles + mt;
+        pend_it = it;
       }
       XVEC_CNT(e_tail += clock64() - e_t0;)
       item = next_item;
