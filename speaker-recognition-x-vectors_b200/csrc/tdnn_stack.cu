@@ -54,12 +54,15 @@ namespace xvec {
 // Measured: MMA-warp cycles per TDNN2/3 tile 9 / 10 / 11 / 12 slots: 16 480 / 14 050 / 13 540 / 13 090; whole launch 326.8 /
 // 299.2 / 295.8 / 297.1 us (debug builds) — the launch as a whole gains 1-2 % over the separate rings, within box-to-box spread.
 // Shared memory per CTA: 1 KiB alignment slack + the ring + the TMA-store staging of the 8 epilogue warps.  bf16 activations:
-// 11 slots + one 2 KiB box (32 rows x 64 bytes) per warp = 204 KiB; float32 activations: 10 slots + one 4 KiB box (32 rows x
+// 10 slots + two 2 KiB boxes (32 rows x 64 bytes) per warp = 203 KiB (until the last sessions: 11 slots + one box = 204 KiB); float32 activations: 10 slots + one 4 KiB box (32 rows x
 // 128 bytes) = 203 KiB.  NOT the 227 KiB a CTA could have: the kernels of a batch's tail (pooling finalize + segment layers)
 // must fit on the SM NEXT TO a resident CTA of the next batch's stack kernel (about 20 KiB of shared memory and 20 K registers
 // stay free), otherwise they wait for a whole stack kernel to drain — measured in round 1: ~24 us of a 325 us step.  Measured
 // here (256 x 300, bf16, us per launch on one box): 12 slots / 1 box 290.5, 11 / 2 boxes 291.9, 11 / 1 box 292.2 — the last
 // slot buys less than the co-residency it would cost.
+// Last sessions of round 2 (after the fences / publication were made cheap, so that the store epilogue weighs more): 10 slots + TWO
+// boxes per warp (staging chunk k+1 while the store of chunk k still reads its box) 262.8 us against 11 slots + one box 263.7
+// (64 x 6000: 1 297 vs 1 303) — 203 KiB, the default now; the wait for the box's previous store sits after the chunk's math.
 // XVEC_MMA_FIXED = 1: the MMA warp runs the K loop specialised at compile time for the tap counts the x-vector stack has
 // (mma_tile_fixed); 0: the generic loop for every layer (mma_tile).  Same MMAs in the same order either way.
 #ifndef XVEC_MMA_FIXED
@@ -73,10 +76,13 @@ namespace xvec {
 #ifndef XVEC_PUBLISH_PER_CTA
 #define XVEC_PUBLISH_PER_CTA 1  // one gpu-scope release per stored tile and CTA (the last of its 8 epilogue warps) instead of one per warp
 #endif
+#ifndef XVEC_LATE_WAIT_READ
+#define XVEC_LATE_WAIT_READ 1
+#endif
 #ifndef XVEC_RING_SLOTS_BF16
-#define XVEC_RING_SLOTS_BF16 11
+#define XVEC_RING_SLOTS_BF16 10
 #define XVEC_RING_SLOTS_F32 10
-#define XVEC_STAGE_BOXES_BF16 1
+#define XVEC_STAGE_BOXES_BF16 2
 #endif
 template <bool kAllTf32>
 struct StackCfg {
@@ -730,8 +736,10 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
           uint32_t(&v)[32] = (k & 1) ? vb : va;
           if (k + 1 < BOXES) tmem_ld_32x32(tbase + cbeg + 32 * (k + 1), (k & 1) ? va : vb);
           uint8_t* ob = out_stage + (store_seq % NBUF) * BOX_BYTES;
+#if !XVEC_LATE_WAIT_READ
           if (lane == 0) tma_store_wait_read<NBUF - 1>();  // the store that last used this box has read it
           __syncwarp();
+#endif
           const int col0 = n0 + cbeg + k * 32;
           // r = relu(acc + bias') — every BatchNorm is folded forward into the next layer's weights (xvector.py)
           float o[32];
@@ -743,6 +751,11 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
             const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), make_float2(bb.z, bb.w));
             o[j4 + 0] = a.x; o[j4 + 1] = a.y; o[j4 + 2] = d.x; o[j4 + 3] = d.y;
           }
+#if XVEC_LATE_WAIT_READ
+          // the store that last used this box must have read it — checked only now, after the bias / ReLU math of this chunk
+          if (lane == 0) tma_store_wait_read<NBUF - 1>();
+          __syncwarp();
+#endif
           // row `lane` of the box, 16-byte pieces XOR-swizzled like the tensor map's swizzle mode expects
           uint8_t* orow = ob + lane * BOX_W;
           if constexpr (!kAllTf32) {  // SWIZZLE_64B: piece index ^ address bits [7,9) = (row / 2) % 4
