@@ -43,16 +43,16 @@ SEG6_FLOPS = 3_072_000
 LAUNCHES_PER_BATCH = 3  # tdnn_stack_kernel, pool_finalize_kernel, fc_small_kernel (segment6)
 LONG_BATCHES = 2048     # the "long" legs: ~0.6 s of bf16 work per GPU
 WORKLOAD = "c2: 1024 x 3 s utterances (300 x 24 MFCC) per step and GPU as 4 batches of 256, x_vec_extract_layer 6"
-NCU_TENSOR_PIPE = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 77.1, "file": "profiles/r02d_stack_ncu_full_summary.txt",
-                   "note": "ncu --set full capture of one tdnn_stack_kernel launch of the final code (cold, serialised, 260.7 us at 1.73 GHz = 452 k "
-                           "cycles; the capture before the last K-loop change: 78.3 % at 1.60 GHz, 445 k cycles); ~7 % of the issued "
+NCU_TENSOR_PIPE = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 84.1, "file": "profiles/r02f_stack_ncu_full_summary.txt",
+                   "note": "ncu --set full capture of one tdnn_stack_kernel launch of the final code (cold, serialised, 241.5 us at 1.72 GHz = 414 k "
+                           "cycles; before the last session's fence / hand-off / publication changes: 77.1-78.3 %, 445-452 k cycles); ~7 % of the issued "
                            "MMA work is padding (don't-care rows of the flat layout, N 1500 -> 1536, K 120 -> 128)"}
-NCU_TENSOR_PIPE_TF32 = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 87.4, "file": "profiles/r02d_stack_tf32_ncu_full_summary.txt",
-                        "note": "ncu --set full capture of one tdnn_stack_kernel<tf32> launch of the final code (486.3 us at 1.60 GHz)"}
+NCU_TENSOR_PIPE_TF32 = {"sm__pipe_tensor_cycles_active_pct_of_elapsed": 87.4, "file": "profiles/r02f_stack_tf32_ncu_full_summary.txt",
+                        "note": "ncu --set full capture of one tdnn_stack_kernel<tf32> launch of the final code (471.2 us at 1.65 GHz)"}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tdnn_stack_kernel launch on this workload (ncu --set full; see profiles/README.md)
-STACK_DRAM_BYTES = {"bf16": 183326976,   # 16.8 MB read + 166.5 MB written (final contents of the activation buffers)
-                    "tf32": 690584576}   # 106.2 MB read + 584.4 MB written: float32 activations of a band do not fit in L2
-STACK_DRAM_SOURCE = {"bf16": "profiles/r02d_stack_ncu_full_summary.txt", "tf32": "profiles/r02d_stack_tf32_ncu_full_summary.txt"}
+STACK_DRAM_BYTES = {"bf16": 186766336,   # 17.8 MB read + 169.0 MB written (final contents of the activation buffers)
+                    "tf32": 713932032}   # 125.3 MB read + 588.6 MB written: float32 activations of a band do not fit in L2
+STACK_DRAM_SOURCE = {"bf16": "profiles/r02f_stack_ncu_full_summary.txt", "tf32": "profiles/r02f_stack_tf32_ncu_full_summary.txt"}
 
 
 def flops_per_utt(t):
