@@ -6,15 +6,16 @@
 //
 //   * dynamic tile scheduler: a scheduler warp in the leader CTA of each pair draws the next item with one atomicAdd on a global
 //     counter (while the current tile is loading) and hands it to all warp roles of both CTAs through a small shared-memory ring
-//     (mbarrier full/empty, the peer's copy written with st.shared::cluster + release/acquire at cluster scope).  Items are
+//     (mbarrier full/empty; the peer's copy travels as an st.async that completes a transaction on the peer's barrier).  Items are
 //     drawn strictly in order and an item only depends on EARLIER items, so any number of resident CTAs makes progress —
 //     two of these kernels on two streams cannot deadlock each other.
 //   * item order: bands of `band` m-tiles; inside a band layer 1, 2, ... L, the m-range of layer l skewed down by l tiles
 //     (layer l+1 tile m reads layer l tiles m-1.. m+1, all in the same or an earlier band).  Bands of ~2.3 x pairs m-tiles are
 //     long enough that an item's inputs are complete when it is drawn and short enough that a band's activations stay in L2
 //     between the layers (see pick_band).
-//   * inter-layer dependencies: every epilogue warp adds 1 to ready[layer][m_tile] (red.release.gpu) once its TMA stores of
-//     that tile are COMPLETE (cp.async.bulk.wait_group, deferred so that it never blocks a busy warp); a dependency warp per
+//   * inter-layer dependencies: once the TMA stores of a tile are COMPLETE (cp.async.bulk.wait_group per epilogue warp, deferred
+//     so that it never blocks a busy warp) the last of a CTA's eight epilogue warps adds 8 to ready[layer][m_tile]
+//     (fence.proxy.async.global + red.release.gpu: ONE gpu-scope release per tile and CTA); a dependency warp per
 //     CTA runs ahead of the TMA producer, polls (ld.acquire.gpu) the flags of the tiles the next items touch and hands each
 //     item to the producer through an mbarrier, so flag latency and the proxy fence stay off the load path.
 //     The two ping-pong activation buffers are safe: tile (l, m) overwrites rows whose readers (l-1, m-1) and (l-1, m) it
