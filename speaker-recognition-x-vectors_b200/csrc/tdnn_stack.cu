@@ -478,7 +478,8 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (rank == 0) {
       MmaRing<RING_SLOTS> ring;
-      unsigned long long c_full = 0, c_tempty = 0, c_step = 0, c_ring = 0;
+      unsigned long long c_full = 0, c_step = 0;  // debug counters (explicit operand waits / time inside the issue step)
+      XVEC_CNT(unsigned long long c_tempty = 0, c_ring = 0;)
       for (int it = 0;; ++it) {
         XVEC_CNT(const long long tr = clock64();)
         const uint32_t item = ring_read(it);
@@ -607,7 +608,6 @@ tdnn_stack_kernel(const __grid_constant__ StackMaps maps, const __grid_constant_
     // ------------------------------------------------------------------ epilogue warps (both CTAs, 128 rows each)
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
     const int cbeg = ((warp - 2) >> 2) * (BN / 2);  // this warp's half of the tile's columns
-    const int cend = cbeg + BN / 2;
     uint8_t* out_stage = epi_smem + (warp - 2) * StackCfg<kAllTf32>::STAGE_BYTES;
     int store_seq = 0;
     // Store staging: one TMA-store box per tcgen05.ld chunk (32 rows x 32 columns).  bf16: 64-byte rows (SWIZZLE_64B), the warp's
